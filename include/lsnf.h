@@ -1,0 +1,186 @@
+/*
+ * lsnf.h -- C ABI of the B200-native short-run Langevin posterior-inference path.
+ *
+ * The reference (jianwen-xie/Latent-Space-Normalizing-Flow) is pure Python and has no FFI; the entry
+ * points below are what a binding for its hot path would call, one per reference call site
+ * (paths relative to the reference tree):
+ *
+ *   lsnf_generator_forward   <- netG(z)                                   train.py:312, model.py:156-157
+ *   lsnf_generator_dgrad     <- torch.autograd.grad(g_log_lkhd, z)        train.py:313-314
+ *   lsnf_flow_forward        <- netF(z, objective) + log-prior + its grad train.py:316-323, model.py:473-483
+ *   lsnf_flow_inverse        <- netF(z, objective, reverse=True)          train.py:434, :569; model.py:484-498
+ *   lsnf_langevin_update     <- z update + noise + diagnostics            train.py:324-329
+ *   lsnf_langevin_run        <- sample_langevin_post_z_with_flow          train.py:307-335, :602-634
+ *   lsnf_pack_*              <- parameters of _netG / _netF               model.py:48-157, :460-498
+ *
+ * Conventions: every function returns 0 on success and a negative lsnf_status otherwise;
+ * lsnf_last_error() returns a thread-local message for the last failure.  All tensor arguments are raw
+ * DEVICE pointers to contiguous fp32 data in the reference's own layouts (NCHW images, [B,nz] latents,
+ * [C_in,C_out,k,k] ConvTranspose2d weights) unless stated otherwise.  `stream` is a cudaStream_t; all work
+ * is enqueued on it and no call synchronises the device.  The caller owns every buffer, including the
+ * workspace; inputs are never modified.  A plan is tied to one device and one batch size and is not
+ * thread-safe; distinct plans may be used concurrently from distinct threads / streams.
+ *
+ * There is no CPU fallback: on a machine without a CUDA device every compute entry point fails with
+ * LSNF_ERR_CUDA.
+ */
+#ifndef LSNF_H_
+#define LSNF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSNF_ABI_VERSION 1
+
+typedef struct lsnf_plan lsnf_plan;
+typedef void* lsnf_stream; /* cudaStream_t */
+
+typedef enum lsnf_status {
+  LSNF_OK = 0,
+  LSNF_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  LSNF_ERR_CUDA = -2,        /* CUDA runtime or driver error (message has the detail) */
+  LSNF_ERR_STATE = -3,       /* call order violated (e.g. weights not packed, workspace not bound) */
+  LSNF_ERR_UNSUPPORTED = -4  /* configuration the reference itself rejects or never implemented */
+} lsnf_status;
+
+/* generator architectures of model.py:52-151 (args.dataset) */
+typedef enum lsnf_arch {
+  LSNF_ARCH_NONE = -1,        /* flow prior only (no generator stages) */
+  LSNF_ARCH_SVHN = 0,         /* model.py:56-71  */
+  LSNF_ARCH_CIFAR10 = 1,      /* model.py:77-92  */
+  LSNF_ARCH_CELEBA_CROP = 2,  /* model.py:98-117 */
+  LSNF_ARCH_CELEBA_HQ256 = 3  /* model.py:123-151 */
+} lsnf_arch;
+
+typedef enum lsnf_gemm_impl {
+  LSNF_GEMM_TCGEN05 = 0, /* product path: TMA-fed tcgen05 tensor-core tiles, bf16 hi/lo split, 3 passes */
+  LSNF_GEMM_SIMT = 1     /* debugging twin on CUDA cores over the same buffers (tests only) */
+} lsnf_gemm_impl;
+
+typedef struct lsnf_config {
+  int32_t arch;          /* lsnf_arch */
+  int32_t batch;         /* samples held by this plan (this rank's shard) */
+  int32_t nz;            /* --nz, even (model.py:383) */
+  int32_t ngf;           /* --ngf */
+  int32_t nc;            /* --nc (3) */
+  int32_t f_depth;       /* --f_depth */
+  int32_t f_width;       /* --f_width */
+  int32_t f_permutation; /* --f_flow_permutation: 2 = invertible 1x1 (default), 1 = fixed shuffle */
+  int32_t f_coupling;    /* --f_flow_coupling: 1 = affine (default), 0 = additive */
+  float leak;            /* --g_activation_leak of the LeakyReLU (0.2) */
+  int32_t gemm_impl;     /* lsnf_gemm_impl */
+  int32_t reserved[5];
+} lsnf_config;
+
+/* number of per-step flow parameter pointers expected by lsnf_pack_flow_weights, in this order:
+ * actnorm.b, actnorm.logs, invertible_1x1_conv.w, f.fc_1.w, f.fc_1.actnorm.b, f.fc_1.actnorm.logs,
+ * f.fc_2.w, f.fc_2.actnorm.b, f.fc_2.actnorm.logs, f.fc_zeros.w, f.fc_zeros.b, f.fc_zeros.logs
+ * (state_dict names under revnet2d_s.0.revnet2d_step_s.<i>., model.py:367-387) */
+#define LSNF_FLOW_PTRS_PER_STEP 12
+
+int lsnf_abi_version(void);
+const char* lsnf_last_error(void);
+
+/* ---- plan ------------------------------------------------------------------------------------------- */
+/* Pure host work: validates the configuration, lays out the workspace and builds the stage tables. */
+int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out);
+void lsnf_plan_destroy(lsnf_plan* plan);
+size_t lsnf_workspace_bytes(const lsnf_plan* plan);
+/* `workspace` is device memory of at least lsnf_workspace_bytes(), 1024-byte aligned, zero-initialised by
+ * the caller once.  Encodes the TMA descriptors that point into it. */
+int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes);
+
+/* ---- parameters ------------------------------------------------------------------------------------- */
+/* weights[i]: [C_in,C_out,k,k], biases[i]: [C_out] of the i-th ConvTranspose2d (gen.{3i}.weight|bias).
+ * Re-packs into the bf16 hi/lo K-major operand layouts of every forward and data-gradient stage. */
+int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* weights, const float* const* biases,
+                                int32_t n_layers, lsnf_stream stream);
+/* params: f_depth * LSNF_FLOW_PTRS_PER_STEP device pointers (order above).  For f_permutation == 1 the
+ * third pointer of each step is ignored and perm / perm_inverse hold f_depth device pointers to int32[nz].
+ * log_abs_det: DEVICE array [f_depth] of log|det W_i| evaluated in fp64 as model.py:182 does (ignored for shuffle);
+ * w_inverse: f_depth device pointers to [nz,nz] inverses (model.py:193), or NULL if lsnf_flow_inverse is
+ * not going to be called.  Both are hoisted out of the Langevin loop: parameters are constant during it. */
+int lsnf_pack_flow_weights(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
+                           const int32_t* const* perm_inverse, const float* log_abs_det,
+                           const float* const* w_inverse, lsnf_stream stream);
+
+/* ---- stages of one Langevin step -------------------------------------------------------------------- */
+/* z [B,nz] -> x_hat [B,nc,H,W]; keeps the activations in the workspace for lsnf_generator_dgrad. */
+int lsnf_generator_forward(lsnf_plan* plan, const float* z, float* x_hat, lsnf_stream stream);
+/* grad_z [B,nz] = d/dz [ 1/(2 sigma^2) * sum (G(z) - x)^2 ] for the z of the last lsnf_generator_forward. */
+int lsnf_generator_dgrad(lsnf_plan* plan, const float* x, float sigma, float* grad_z, lsnf_stream stream);
+/* z [B,nz] -> z_out [B,nz], logdet [B], logp [B] (= sum(-z_out^2/2) + log(2 pi) + logdet, train.py:317-319),
+ * grad_z [B,nz] = d/dz [ -sum_b logp_b ] (train.py:320-323).  Any output pointer may be NULL. */
+int lsnf_flow_forward(lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
+                      float* grad_z, lsnf_stream stream);
+/* eps [B,nz] -> z [B,nz] = F^-1(eps); neg_objective [B] (nullable) is what the reference returns with
+ * return_obj=True for objective=0 (model.py:498).  Does not modify eps (the reference does, model.py:436). */
+int lsnf_flow_inverse(lsnf_plan* plan, const float* eps, float* z, float* neg_objective, lsnf_stream stream);
+/* z <- z - s^2/2 (grad_g + grad_f) [+ s * noise]  (train.py:324-326).  noise = eps [B,nz] when eps != NULL,
+ * else (with_noise != 0) Philox4x32-10 keyed by (seed, sample_offset + b, step), else none.
+ * gnorms (nullable, device float[2]) receives mean_b |grad_g_b|_2 and mean_b |grad_f_b|_2 (train.py:328-329). */
+int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad_g, const float* grad_f, float step_size,
+                         const float* eps, int32_t with_noise, uint64_t seed, uint64_t sample_offset,
+                         uint32_t step, float* gnorms, lsnf_stream stream);
+
+/* ---- the whole loop --------------------------------------------------------------------------------- */
+/* sample_langevin_post_z_with_flow: z0 [B,nz], x [B,nc,H,W] -> z_out [B,nz] after `steps` iterations and
+ * gnorms[2] (device) from the last one.  eps: [steps,B,nz] injected noise or NULL; see lsnf_langevin_update.
+ * z0 and z_out may alias. */
+int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t steps, float step_size,
+                      float sigma, int32_t with_noise, const float* eps, uint64_t seed, uint64_t sample_offset,
+                      float* z_out, float* gnorms, lsnf_stream stream);
+/* how many kernels one lsnf_langevin_run of `steps` iterations launches (for bench.py's gpu_launches). */
+int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps);
+
+/* ---- introspection (host only; used by the CPU tests to emulate the stage tables) -------------------- */
+#define LSNF_MAX_TAPS 16
+#define LSNF_MAX_PHASES 4
+
+typedef struct lsnf_tap {
+  int32_t dy, dx; /* shift of the operand box in the stage's row grid */
+  int32_t plane;  /* phase plane of a phase-split operand (0 for plain NHWC) */
+  int32_t brow;   /* first row of this tap's block in the packed weight matrix */
+} lsnf_tap;
+
+typedef struct lsnf_stage_info {
+  int32_t kind;          /* 0 forward, 1 data-gradient */
+  int32_t layer;         /* generator layer index */
+  int32_t grid_h, grid_w;/* row grid: M = batch * grid_h * grid_w */
+  int32_t box_b, box_h, box_w; /* M tile = box_b*box_h*box_w = 128 rows */
+  int32_t k_per_tap;     /* channels contracted per tap (multiple of 64) */
+  int32_t n_valid, n_pad;/* output columns, and padded to the N tile */
+  int32_t block_n;       /* N tile */
+  int32_t n_phases;
+  int32_t n_taps[LSNF_MAX_PHASES];
+  lsnf_tap taps[LSNF_MAX_PHASES][LSNF_MAX_TAPS];
+  int32_t out_mul;       /* output position = row position * out_mul + out_off[phase] */
+  int32_t out_off_y[LSNF_MAX_PHASES], out_off_x[LSNF_MAX_PHASES];
+  int32_t out_phase_split; /* output written in phase-split layout */
+  int32_t out_channels;  /* channels per output position (n_pad may span several positions) */
+  int32_t epilogue;      /* 0 bias+lrelu -> bf16 hi/lo, 1 bias+tanh -> fp32 NCHW, 2 *lrelu' -> bf16 hi/lo, 3 fp32 split-K partial */
+  int32_t k_splits;
+  int32_t a_planes;      /* planes of the A operand (4 when phase-split) */
+  int32_t a_h, a_w;      /* spatial extent of the A operand (== grid except for the first layer's data gradient) */
+  int32_t tap_gen_k;     /* != 0: taps are generated, tap t = (dy, dx) = (t / k, t % k), weight column offset t*k_per_tap */
+  int32_t b_k;           /* columns of the hi half of the packed weight matrix (lo half follows) */
+  int32_t b_rows;        /* rows of the packed weight matrix */
+  int64_t a_offset, b_offset, out_offset; /* byte offsets into the workspace */
+  int64_t flops;         /* 2*M*N*K over all phases and taps (nominal, padded taps included) */
+} lsnf_stage_info;
+
+int lsnf_plan_num_stages(const lsnf_plan* plan);
+int lsnf_plan_stage_info(const lsnf_plan* plan, int32_t index, lsnf_stage_info* out);
+/* (row, col) of ConvTranspose2d weight element W[ci][co][ky][kx] of `layer` inside the packed operand of
+ * stage `index` (hi half; the lo half sits k_total columns further).  Returns <0 if the stage does not use it. */
+int lsnf_plan_pack_index(const lsnf_plan* plan, int32_t index, int32_t ci, int32_t co, int32_t ky, int32_t kx,
+                         int64_t* row, int64_t* col);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSNF_H_ */

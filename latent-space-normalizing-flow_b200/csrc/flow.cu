@@ -1,0 +1,466 @@
+// Fused flow-prior kernels (fp32 CUDA cores): actnorm -> invertible 1x1 (or fixed shuffle) -> coupling,
+// all f_depth steps in one launch, per-sample log-det and log p(z) reduced in-kernel, followed (same launch)
+// by the analytic backward d(-sum_b log p(z_b))/dz.  Reference: model.py:357-365 (revnet2d), :389-458
+// (revnet2d_step), :280-294 (actnorm), :179-198 (invertible_1x1_conv), :306-350 (coupling MLP),
+// train.py:316-323 (log-prior and its gradient).  Backward formulas: SURVEY.md section 8a, row A5
+// (pinned against autograd in fp64 by tests/test_oracle_golden.py).
+#include "lsnf_internal.cuh"
+
+namespace lsnf {
+
+struct FlowArgs {
+  const float* params;  // f_depth blocks of FlowLayout::step_floats
+  FlowLayout fl;
+  int depth, B, coupling, permutation;
+  const float* in;      // z (forward) or eps (inverse), [B][nz]
+  float* z_out;         // forward: z_out; inverse: z
+  float* logdet;        // forward: logdet; inverse: -objective
+  float* logp;
+  float* grad;
+};
+
+constexpr int FLOW_THREADS = 256;
+
+// out[s][j] = epi(s, j, sum_k in[s][k] * M[k*N + j]) for s < S, j < N.  M is row-major [K][N] in global
+// memory (read once per CTA, coalesced along j); `in` and `out` live in shared memory.  The K range is split
+// across 256/Nr thread groups whose partial sums meet in `scratch`.
+template <int S, class Epi>
+__device__ __forceinline__ void matvec(const float* __restrict__ M, int K, int N, const float* in, int ldin,
+                                       float* scratch, Epi epi) {
+  const int Nr = (N + 31) & ~31;
+  const int G = FLOW_THREADS / Nr > 0 ? FLOW_THREADS / Nr : 1;
+  const int tid = threadIdx.x;
+  const int Kc = (K + G - 1) / G;
+  for (int j0 = 0; j0 < N; j0 += FLOW_THREADS) {   // only loops when N > 256 (never: nz, f_width <= 256)
+    const int g = tid / Nr, j = j0 + tid % Nr;
+    if (g < G && j < N) {
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = 0.f;
+      const int k0 = g * Kc, k1 = min(K, k0 + Kc);
+      const float* m = M + (size_t)k0 * N + j;
+#pragma unroll 8
+      for (int k = k0; k < k1; ++k, m += N) {
+        const float w = __ldg(m);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(in[s * ldin + k], w, acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) scratch[(g * S + s) * Nr + (j - j0)] = acc[s];
+    }
+    __syncthreads();
+    for (int i = tid; i < S * Nr; i += FLOW_THREADS) {
+      const int s = i / Nr, jj = i % Nr;
+      if (j0 + jj < N) {
+        float v = 0.f;
+        for (int g2 = 0; g2 < G; ++g2) v += scratch[(g2 * S + s) * Nr + jj];
+        epi(s, j0 + jj, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// sum over the threads of the CTA of one value per sample slot; result valid in thread 0.. (returned to all)
+template <int S>
+__device__ __forceinline__ void block_sum(float (&v)[S], float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[s] += __shfl_xor_sync(0xffffffffu, v[s], o);
+    if (lane == 0) red[warp * S + s] = v[s];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    float t = 0.f;
+    for (int w = 0; w < FLOW_THREADS / 32; ++w) t += red[w * S + s];
+    v[s] = t;
+  }
+  __syncthreads();
+}
+
+template <int S>
+__global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) {
+  extern __shared__ float sm[];
+  const FlowLayout& f = a.fl;
+  const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
+  const int nmax = max(nz, max(w, n_out));
+  const int nr_max = (nmax + 31) & ~31;
+  const int stash_step = 2 * w + nz;  // a1[w], a2[w], scale[half], x2+shift[half]
+  float* cur = sm;                         // [S][nz]
+  float* ta = cur + S * nz;                // [S][nmax]
+  float* tb = ta + S * nmax;               // [S][nmax]
+  float* scratch = tb + S * nmax;          // [256/32*... ] partial sums: G*S*Nr <= 256*S (+ slack)
+  float* red = scratch + S * max(FLOW_THREADS, nr_max);
+  float* stash = red + (FLOW_THREADS / 32) * S;  // [depth][S][stash_step]
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * S;
+  const int ns = min(S, a.B - b0);
+
+  for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+    const int s = i / nz, j = i % nz;
+    cur[i] = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
+  }
+  __syncthreads();
+
+  float ld[S];  // per-thread partial of sum_j log(scale); constants are added by thread 0 only
+#pragma unroll
+  for (int s = 0; s < S; ++s) ld[s] = 0.f;
+
+  for (int L = 0; L < a.depth; ++L) {
+    const float* P = a.params + (size_t)L * f.step_floats;
+    float* st = stash + (size_t)L * S * stash_step;
+    // actnorm (model.py:282-284): (x + b) * exp(3 logs)
+    for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+      const int j = i % nz;
+      ta[(i / nz) * nmax + j] = (cur[i] + P[f.an_b + j]) * P[f.an_e + j];
+    }
+    __syncthreads();
+    if (a.permutation == 2) {   // model.py:187: z @ W
+      matvec<S>(P + f.W, nz, nz, ta, nmax, scratch, [&](int s, int j, float v) { cur[s * nz + j] = v; });
+    } else {                    // intended shuffle_features: h[:, idx]
+      const int* idx = reinterpret_cast<const int*>(P + f.perm);
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) cur[i] = ta[(i / nz) * nmax + idx[i % nz]];
+      __syncthreads();
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) ld[s] += P[f.ld_const] , ld[s] += P[f.ld_const + 1];
+    }
+    // coupling MLP on x1 = cur[:, :half] (model.py:306-310)
+    float* a1 = st;             // [S][w]
+    float* a2 = st + S * w;     // [S][w]
+    float* sc = a2 + S * w;     // [S][half]
+    float* xs = sc + S * half;  // [S][half]
+    matvec<S>(P + f.W1, half, w, cur, nz, scratch,
+              [&](int s, int j, float v) { a1[s * w + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
+    matvec<S>(P + f.W2, w, w, a1, w, scratch,
+              [&](int s, int j, float v) { a2[s * w + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
+    matvec<S>(P + f.W3, w, n_out, a2, w, scratch,
+              [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    if (a.coupling == 1) {      // model.py:410-418
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        const float shift = ta[s * nmax + 2 * j];
+        const float scale = 1.f / (1.f + expf(-(ta[s * nmax + 2 * j + 1] + 2.f)));
+        const float x2s = cur[s * nz + half + j] + shift;
+        cur[s * nz + half + j] = x2s * scale;
+        sc[i] = scale; xs[i] = x2s;
+#pragma unroll
+        for (int q = 0; q < S; ++q) if (q == s) ld[q] += logf(scale);
+      }
+    } else {                    // model.py:407-408
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        cur[s * nz + half + j] += ta[s * nmax + j];
+      }
+    }
+    __syncthreads();
+  }
+
+  // log-det and log p(z) (train.py:317-319), warp-shuffle reductions
+  block_sum<S>(ld, red);
+  float sq[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) sq[s] = 0.f;
+  for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+    const int s = i / nz;
+    const float v = cur[i];
+#pragma unroll
+    for (int q = 0; q < S; ++q) if (q == s) sq[q] += -0.5f * v * v;
+  }
+  block_sum<S>(sq, red);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (s < ns) {
+        if (a.logdet) a.logdet[b0 + s] = ld[s];
+        if (a.logp) a.logp[b0 + s] = sq[s] + 1.8378770664093453f + ld[s];  // log(2 pi), train.py:318
+      }
+    }
+  }
+  if (a.z_out)
+    for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+      const int s = i / nz;
+      if (s < ns) a.z_out[(size_t)(b0 + s) * nz + i % nz] = cur[i];
+    }
+  if (!a.grad) return;
+
+  // ---- analytic backward of -sum_b ll_b: seed g = z_out, d/dlogdet = -1 ----
+  float* g = cur;  // in place
+  for (int L = a.depth - 1; L >= 0; --L) {
+    const float* P = a.params + (size_t)L * f.step_floats;
+    float* st = stash + (size_t)L * S * stash_step;
+    const float* a1 = st;
+    const float* a2 = st + S * w;
+    const float* sc = a2 + S * w;
+    const float* xs = sc + S * half;
+    // gradient w.r.t. the MLP output h, already multiplied by e3 = exp(3 logs_zeros)
+    if (a.coupling == 1) {
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        const float g2 = g[s * nz + half + j], scale = sc[i];
+        const float g_shift = g2 * scale;
+        const float g_scale = g2 * xs[i] - 1.f / scale;
+        ta[s * nmax + 2 * j] = g_shift * P[f.e3 + 2 * j];
+        ta[s * nmax + 2 * j + 1] = g_scale * scale * (1.f - scale) * P[f.e3 + 2 * j + 1];
+        g[s * nz + half + j] = g_shift;  // = g_x2
+      }
+    } else {
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        ta[s * nmax + j] = g[s * nz + half + j] * P[f.e3 + j];
+      }
+    }
+    __syncthreads();
+    matvec<S>(P + f.W3T, n_out, w, ta, nmax, scratch,
+              [&](int s, int j, float v) { tb[s * nmax + j] = a2[s * w + j] > 0.f ? v * P[f.e2 + j] : 0.f; });
+    matvec<S>(P + f.W2T, w, w, tb, nmax, scratch,
+              [&](int s, int j, float v) { ta[s * nmax + j] = a1[s * w + j] > 0.f ? v * P[f.e1 + j] : 0.f; });
+    matvec<S>(P + f.W1T, w, half, ta, nmax, scratch, [&](int s, int j, float v) { g[s * nz + j] += v; });
+    if (a.permutation == 2) {   // g @ W^T, then the actnorm scale
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[(i / nz) * nmax + i % nz] = g[i];
+      __syncthreads();
+      matvec<S>(P + f.WT, nz, nz, ta, nmax, scratch,
+                [&](int s, int j, float v) { g[s * nz + j] = v * P[f.an_e + j]; });
+    } else {
+      const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[(i / nz) * nmax + i % nz] = g[i];
+      __syncthreads();
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+        const int j = i % nz;
+        g[i] = ta[(i / nz) * nmax + inv[j]] * P[f.an_e + j];
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+    const int s = i / nz;
+    if (s < ns) a.grad[(size_t)(b0 + s) * nz + i % nz] = g[i];
+  }
+}
+
+// reverse pass (model.py:424-456, :361-363, :484-498)
+template <int S>
+__global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) {
+  extern __shared__ float sm[];
+  const FlowLayout& f = a.fl;
+  const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
+  const int nmax = max(nz, max(w, n_out));
+  const int nr_max = (nmax + 31) & ~31;
+  float* cur = sm;
+  float* ta = cur + S * nz;
+  float* tb = ta + S * nmax;
+  float* scratch = tb + S * nmax;
+  float* red = scratch + S * max(FLOW_THREADS, nr_max);
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * S;
+  const int ns = min(S, a.B - b0);
+  for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+    const int s = i / nz, j = i % nz;
+    cur[i] = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
+  }
+  __syncthreads();
+  float ld[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) ld[s] = 0.f;
+  for (int L = a.depth - 1; L >= 0; --L) {
+    const float* P = a.params + (size_t)L * f.step_floats;
+    matvec<S>(P + f.W1, half, w, cur, nz, scratch,
+              [&](int s, int j, float v) { ta[s * nmax + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
+    matvec<S>(P + f.W2, w, w, ta, nmax, scratch,
+              [&](int s, int j, float v) { tb[s * nmax + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
+    matvec<S>(P + f.W3, w, n_out, tb, nmax, scratch,
+              [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    if (a.coupling == 1) {      // model.py:432-438
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        const float shift = ta[s * nmax + 2 * j];
+        const float scale = 1.f / (1.f + expf(-(ta[s * nmax + 2 * j + 1] + 2.f)));
+        cur[s * nz + half + j] = cur[s * nz + half + j] / scale - shift;
+#pragma unroll
+        for (int q = 0; q < S; ++q) if (q == s) ld[q] -= logf(scale);
+      }
+    } else {                    // model.py:429-430
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        cur[s * nz + half + j] -= ta[s * nmax + j];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < S * nz; i += FLOW_THREADS) tb[(i / nz) * nmax + i % nz] = cur[i];
+    __syncthreads();
+    if (a.permutation == 2) {   // model.py:193-196: z @ inverse(W), then actnorm reverse (:288-291)
+      matvec<S>(P + f.Winv, nz, nz, tb, nmax, scratch,
+                [&](int s, int j, float v) { cur[s * nz + j] = v * P[f.an_ei + j] - P[f.an_b + j]; });
+    } else {
+      const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+        const int j = i % nz;
+        cur[i] = tb[(i / nz) * nmax + inv[j]] * P[f.an_ei + j] - P[f.an_b + j];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) ld[s] -= P[f.ld_const + 1], ld[s] -= P[f.ld_const];
+    }
+  }
+  block_sum<S>(ld, red);
+  if (tid == 0 && a.logdet) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if (s < ns) a.logdet[b0 + s] = -ld[s];   // the reference returns -objective (model.py:498)
+  }
+  for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+    const int s = i / nz;
+    if (s < ns) a.z_out[(size_t)(b0 + s) * nz + i % nz] = cur[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parameter packing: one launch per flow step; builds transposes, exp(+-3 logs) and the log-det constants
+// ---------------------------------------------------------------------------------------------------
+struct FlowPackPtrs {
+  const float* p[LSNF_FLOW_PTRS_PER_STEP];
+  const float* winv;
+  const int32_t* perm;
+  const int32_t* perm_inv;
+  const float* log_abs_det;  // device scalar (nullptr -> 0)
+};
+
+__global__ void flow_pack_kernel(FlowPackPtrs q, FlowLayout f, float* __restrict__ out, int permutation) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
+  for (int i = tid; i < nz; i += nt) {
+    out[f.an_b + i] = q.p[0][i];
+    out[f.an_e + i] = expf(q.p[1][i] * 3.f);
+    out[f.an_ei + i] = expf(-(q.p[1][i] * 3.f));
+    if (permutation == 1) {
+      reinterpret_cast<int*>(out + f.perm)[i] = q.perm[i];
+      reinterpret_cast<int*>(out + f.perm_inv)[i] = q.perm_inv[i];
+    }
+  }
+  if (permutation == 2)
+    for (int i = tid; i < nz * nz; i += nt) {
+      const int r = i / nz, c = i % nz;
+      out[f.W + i] = q.p[2][i];
+      out[f.WT + (size_t)c * nz + r] = q.p[2][i];
+      if (q.winv) out[f.Winv + i] = q.winv[i];
+    }
+  for (int i = tid; i < half * w; i += nt) {
+    const int r = i / w, c = i % w;
+    out[f.W1 + i] = q.p[3][i];
+    out[f.W1T + (size_t)c * half + r] = q.p[3][i];
+  }
+  for (int i = tid; i < w * w; i += nt) {
+    const int r = i / w, c = i % w;
+    out[f.W2 + i] = q.p[6][i];
+    out[f.W2T + (size_t)c * w + r] = q.p[6][i];
+  }
+  for (int i = tid; i < w * n_out; i += nt) {
+    const int r = i / n_out, c = i % n_out;
+    out[f.W3 + i] = q.p[9][i];
+    out[f.W3T + (size_t)c * w + r] = q.p[9][i];
+  }
+  for (int i = tid; i < w; i += nt) {
+    out[f.b1 + i] = q.p[4][i]; out[f.e1 + i] = expf(q.p[5][i] * 3.f);
+    out[f.b2 + i] = q.p[7][i]; out[f.e2 + i] = expf(q.p[8][i] * 3.f);
+  }
+  for (int i = tid; i < n_out; i += nt) {
+    out[f.b3 + i] = q.p[10][i]; out[f.e3 + i] = expf(q.p[11][i] * 3.f);
+  }
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < nz; ++i) s += q.p[1][i] * 3.f;   // torch.sum(logs * 3), model.py:264-273
+    out[f.ld_const] = s;
+    out[f.ld_const + 1] = q.log_abs_det ? *q.log_abs_det : 0.f;
+  }
+}
+
+int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
+                     const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,
+                     cudaStream_t s) {
+  const FlowLayout& f = plan->fl;
+  for (int i = 0; i < plan->cfg.f_depth; ++i) {
+    FlowPackPtrs q;
+    for (int k = 0; k < LSNF_FLOW_PTRS_PER_STEP; ++k) q.p[k] = params[i * LSNF_FLOW_PTRS_PER_STEP + k];
+    q.winv = winv ? winv[i] : nullptr;
+    q.perm = perm ? perm[i] : nullptr;
+    q.perm_inv = perm_inv ? perm_inv[i] : nullptr;
+    q.log_abs_det = plan->cfg.f_permutation == 2 ? log_abs_det + i : nullptr;
+    flow_pack_kernel<<<32, 256, 0, s>>>(q, f, (float*)(plan->ws + plan->off_flow) + (size_t)i * f.step_floats,
+                                        plan->cfg.f_permutation);
+    LSNF_CUDA(cudaGetLastError());
+  }
+  return LSNF_OK;
+}
+
+static int pick_s(int B) {
+  if (B <= 160) return 1;
+  if (B <= 600) return 2;
+  if (B <= 2400) return 4;
+  return 8;
+}
+
+static size_t flow_smem_floats(const FlowLayout& f, int S, int depth, bool stash) {
+  const int nmax = std::max(f.nz, std::max(f.w, f.n_out));
+  const int nr_max = (nmax + 31) & ~31;
+  size_t n = (size_t)S * f.nz + 2 * (size_t)S * nmax + (size_t)S * std::max(FLOW_THREADS, nr_max) +
+             (size_t)(FLOW_THREADS / 32) * S;
+  if (stash) n += (size_t)depth * S * (2 * f.w + f.nz);
+  return n;
+}
+
+template <int S>
+static int launch_fwd_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flow_forward_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+template <int S>
+static int launch_inv_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
+  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flow_inverse_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
+                        float* grad_z, cudaStream_t s) {
+  FlowArgs a;
+  a.params = (const float*)(plan->ws + plan->off_flow);
+  a.fl = plan->fl; a.depth = plan->cfg.f_depth; a.B = plan->cfg.batch;
+  a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
+  a.in = z; a.z_out = z_out; a.logdet = logdet; a.logp = logp; a.grad = grad_z;
+  const int S = pick_s(a.B);
+  const size_t smem = flow_smem_floats(a.fl, S, a.depth, true) * 4;
+  if (smem > 220 * 1024) { set_error("flow kernel shared memory budget exceeded"); return LSNF_ERR_INVALID; }
+  switch (S) {
+    case 1: return launch_fwd_t<1>(a, smem, s);
+    case 2: return launch_fwd_t<2>(a, smem, s);
+    case 4: return launch_fwd_t<4>(a, smem, s);
+    default: return launch_fwd_t<8>(a, smem, s);
+  }
+}
+
+int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s) {
+  FlowArgs a;
+  a.params = (const float*)(plan->ws + plan->off_flow);
+  a.fl = plan->fl; a.depth = plan->cfg.f_depth; a.B = plan->cfg.batch;
+  a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
+  a.in = eps; a.z_out = z; a.logdet = negobj; a.logp = nullptr; a.grad = nullptr;
+  const int S = pick_s(a.B);
+  const size_t smem = flow_smem_floats(a.fl, S, a.depth, false) * 4;
+  switch (S) {
+    case 1: return launch_inv_t<1>(a, smem, s);
+    case 2: return launch_inv_t<2>(a, smem, s);
+    case 4: return launch_inv_t<4>(a, smem, s);
+    default: return launch_inv_t<8>(a, smem, s);
+  }
+}
+
+}  // namespace lsnf

@@ -1,0 +1,162 @@
+// Internal structures shared by the host plan code and the kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "lsnf.h"
+
+namespace lsnf {
+
+constexpr int BLOCK_M = 128;  // rows (batch x grid positions) per tile
+constexpr int BLOCK_K = 64;   // bf16 channels per K block = one 128-byte swizzle span
+
+enum Epilogue : int32_t {
+  EPI_ACT_HL = 0,    // + bias, LeakyReLU, split to bf16 hi|lo                 (hidden forward layers)
+  EPI_OUT_TANH = 1,  // + bias, tanh, fp32 NCHW                                 (last forward layer)
+  EPI_GRAD_HL = 2,   // * LeakyReLU'(saved activation), split to bf16 hi|lo     (hidden data-gradient layers)
+  EPI_PARTIAL = 3    // raw fp32 split-K partial [split][B][n_pad]              (first layer's data gradient)
+};
+
+struct TapDev {
+  int16_t dy, dx, plane, pad_;
+  int32_t brow;
+};
+
+struct PhaseDev {
+  int32_t ntaps;
+  int32_t mo, no;  // output position offset of this phase
+  TapDev taps[LSNF_MAX_TAPS];
+};
+
+// One tap-GEMM launch: D[row, n] = sum_taps sum_k A[plane][b][m+dy][n+dx][k] * Bmat[brow + n][k]
+// with A, Bmat stored as bf16 hi|lo halves (value = hi + lo) concatenated along the channel axis.
+struct StageDev {
+  const __nv_bfloat16* a;  // [aP][B][Hg][Wg][2*Ka]
+  const __nv_bfloat16* b;  // [b_rows][2*Ka]
+  int32_t aP, B, Hg, Wg, Ka, b_rows;
+  int32_t aH, aW, tap_gen, b_k;      // A spatial extent, generated-tap mode (k), hi-half width of B
+  int32_t bB, bH, bW;                // M tile box, bB*bH*bW == 128
+  int32_t tiles_b, tiles_h, tiles_w; // M tiles per axis
+  int32_t n_valid, n_pad, block_n;
+  int32_t nphase, ksplit, it_per_split;
+  // epilogue
+  int32_t epi, bias_mod, oC, ms, split;
+  float leak;
+  const float* bias;
+  void* out;
+  const __nv_bfloat16* mask;          // saved activation [B][Hg][Wg][2*oC] (EPI_GRAD_HL)
+  int64_t sP, sB, sH, sW, sPos;       // output strides in elements
+  int32_t nc, Ho, Wo, pad_;
+  PhaseDev ph[LSNF_MAX_PHASES];
+};
+
+struct StageHost {
+  lsnf_stage_info info;
+  StageDev dev;
+  CUtensorMap tmA, tmB;
+  bool maps_ready = false;
+  int layer = 0;
+  int kind = 0;      // 0 fwd, 1 bwd
+  int k = 0, s = 0, p = 0, ci = 0, co = 0;  // the ConvTranspose2d this stage belongs to
+  size_t a_off = 0, b_off = 0, out_off = 0, mask_off = 0, bias_off = 0;
+  size_t b_bytes = 0;
+  bool last = false, first = false;
+};
+
+struct FlowLayout {
+  // float offsets inside one step's packed block
+  int nz, w, n_out, half;
+  size_t an_b, an_e, an_ei, W, WT, Winv, W1, W1T, b1, e1, W2, W2T, b2, e2, W3, W3T, b3, e3, perm, perm_inv, ld_const;
+  size_t step_floats;
+};
+
+}  // namespace lsnf
+
+struct lsnf_plan {
+  lsnf_config cfg;
+  int n_layers = 0;
+  int img = 0;
+  int kp = 0;   // nz rounded up to BLOCK_K
+  int nzp = 0;  // nz rounded up to 128 (N tile of the first layer's data gradient)
+  struct Layer { int ci, co, k, s, p, hin, hout; } layers[8];
+  std::vector<lsnf::StageHost> stages;  // forward stages 0..L-1, then data-gradient stages L-1..0
+  lsnf::FlowLayout fl;
+  // workspace layout (byte offsets)
+  size_t ws_bytes = 0;
+  size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
+  size_t off_bias[8] = {0};
+  size_t off_norms = 0;
+  size_t off_gradg = 0, off_gradf = 0, off_z = 0, off_flow = 0, off_scalars = 0, off_flow_out = 0;
+  int ksplit_first = 1;
+  char* ws = nullptr;
+  bool bound = false, g_packed = false, f_packed = false, have_winv = false;
+  int device = -1;
+  int num_sms = 148;
+};
+
+namespace lsnf {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define LSNF_CUDA(call)                                       \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return ::lsnf::cuda_fail(e__, #call); \
+  } while (0)
+
+// kernels / launchers implemented in the other translation units
+int launch_tapgemm_simt(const StageHost& st, cudaStream_t s);
+int launch_tapgemm_tc(const StageHost& st, cudaStream_t s);
+int tc_encode_maps(lsnf_plan* plan, StageHost& st);
+int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w, cudaStream_t s);
+int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
+int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
+int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s);
+int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
+                     const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,
+                     cudaStream_t s);
+int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
+                        float* grad_z, cudaStream_t s);
+int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s);
+int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit,
+                  const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
+                  uint64_t sample_offset, uint32_t step_idx, const uint32_t* step_ctr, float* gnorms,
+                  int write_zhl, cudaStream_t s);
+
+// (row, col) of W[ci][co][ky][kx] in the packed B operand of a stage; shared by host and device
+struct PackGeom {
+  int kind, first, last, k, ci, co, n_pad, ka;  // ka = columns of the hi half
+};
+
+__host__ __device__ inline bool pack_index(const PackGeom& g, int ci, int co, int ky, int kx, long long* row,
+                                           long long* col) {
+  const int tap = ky * g.k + kx;
+  if (g.kind == 0) {
+    if (g.first) {  // rows = (tap, co), cols = ci
+      *row = (long long)tap * g.co + co;
+      *col = ci;
+    } else {        // rows = tap * n_pad + co, cols = ci
+      *row = (long long)tap * g.n_pad + co;
+      *col = ci;
+    }
+  } else {
+    if (g.first) {  // rows = ci, cols = (tap, co): K runs over the flattened NHWC activation
+      *row = ci;
+      *col = (long long)tap * g.co + co;
+    } else if (g.last) {  // rows = ci, cols = tap * nc + co (explicit im2col operand)
+      *row = ci;
+      *col = (long long)tap * g.co + co;
+    } else {        // rows = tap * n_pad + ci, cols = co
+      *row = (long long)tap * g.n_pad + ci;
+      *col = co;
+    }
+  }
+  return true;
+}
+
+}  // namespace lsnf

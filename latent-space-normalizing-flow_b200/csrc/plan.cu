@@ -1,0 +1,549 @@
+// Host side of the C ABI: plan construction (stage tables, workspace layout) and the entry points.
+// Reference call sites are cited in include/lsnf.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "lsnf_internal.cuh"
+
+namespace lsnf {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return LSNF_ERR_CUDA;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+
+// model.py:52-151
+static int arch_layers(const lsnf_config& c, lsnf_plan::Layer* L) {
+  const int nz = c.nz, g = c.ngf, nc = c.nc;
+  auto set = [&](int i, int ci, int co, int k, int s, int p) { L[i] = {ci, co, k, s, p, 0, 0}; };
+  switch (c.arch) {
+    case LSNF_ARCH_NONE:
+      return 0;
+    case LSNF_ARCH_SVHN:
+      set(0, nz, g * 8, 4, 1, 0); set(1, g * 8, g * 4, 4, 2, 1); set(2, g * 4, g * 2, 4, 2, 1);
+      set(3, g * 2, nc, 4, 2, 1);
+      return 4;
+    case LSNF_ARCH_CIFAR10:
+      set(0, nz, g * 8, 8, 1, 0); set(1, g * 8, g * 4, 4, 2, 1); set(2, g * 4, g * 2, 4, 2, 1);
+      set(3, g * 2, nc, 3, 1, 1);
+      return 4;
+    case LSNF_ARCH_CELEBA_CROP:
+      set(0, nz, g * 8, 4, 1, 0); set(1, g * 8, g * 4, 4, 2, 1); set(2, g * 4, g * 2, 4, 2, 1);
+      set(3, g * 2, g, 4, 2, 1); set(4, g, nc, 4, 2, 1);
+      return 5;
+    case LSNF_ARCH_CELEBA_HQ256:
+      set(0, nz, g * 16, 4, 1, 0); set(1, g * 16, g * 8, 4, 2, 1); set(2, g * 8, g * 4, 4, 2, 1);
+      set(3, g * 4, g * 2, 4, 2, 1); set(4, g * 2, g, 4, 2, 1); set(5, g, g, 4, 2, 1); set(6, g, nc, 4, 2, 1);
+      return 7;
+    default:
+      return -1;
+  }
+}
+
+static int pick_block_n(int n) {
+  if (n % 256 == 0) return 256;
+  if (n % 128 == 0) return 128;
+  return 64;
+}
+
+static void make_box(int hg, int wg, int* bb, int* bh, int* bw) {
+  *bw = std::min(wg, BLOCK_M);
+  *bh = std::min(hg, BLOCK_M / *bw);
+  *bb = BLOCK_M / (*bw * *bh);
+}
+
+// taps of a k4/s2/p1 transposed convolution for output parity (py, px): oy = 2*iy - 1 + ky
+static int up2_fwd_taps(int py, int px, int n_pad, lsnf_tap* t) {
+  int n = 0;
+  for (int ky = 0; ky < 4; ++ky) {
+    if (((ky + 1) & 1) != py) continue;  // oy + 1 - ky must be even
+    const int dy = (py + 1 - ky) / 2;    // iy = m + dy for oy = 2m + py
+    for (int kx = 0; kx < 4; ++kx) {
+      if (((kx + 1) & 1) != px) continue;
+      const int dx = (px + 1 - kx) / 2;
+      t[n++] = {dy, dx, 0, (ky * 4 + kx) * n_pad};
+    }
+  }
+  return n;
+}
+
+// data gradient of the same layer: gin[iy] = sum_ky g[2*iy - 1 + ky] * W[ky]; g is stored phase-split
+static int up2_bwd_taps(int n_pad, lsnf_tap* t) {
+  int n = 0;
+  for (int ky = 0; ky < 4; ++ky) {
+    const int oy_off = ky - 1;                       // oy = 2*iy + oy_off
+    const int py = oy_off & 1, dy = (oy_off - py) / 2;
+    for (int kx = 0; kx < 4; ++kx) {
+      const int ox_off = kx - 1;
+      const int px = ox_off & 1, dx = (ox_off - px) / 2;
+      t[n++] = {dy, dx, py * 2 + px, (ky * 4 + kx) * n_pad};
+    }
+  }
+  return n;
+}
+
+static void fill_dev(lsnf_plan* p, StageHost& st) {
+  const lsnf_stage_info& I = st.info;
+  StageDev& d = st.dev;
+  memset(&d, 0, sizeof(d));
+  d.aP = I.a_planes; d.B = p->cfg.batch; d.Hg = I.grid_h; d.Wg = I.grid_w; d.Ka = I.k_per_tap;
+  d.bB = I.box_b; d.bH = I.box_h; d.bW = I.box_w;
+  d.aH = I.a_h; d.aW = I.a_w; d.tap_gen = I.tap_gen_k; d.b_k = I.b_k; d.b_rows = I.b_rows;
+  d.tiles_b = (d.B + d.bB - 1) / d.bB; d.tiles_h = d.Hg / d.bH; d.tiles_w = d.Wg / d.bW;
+  d.n_valid = I.n_valid; d.n_pad = I.n_pad; d.block_n = I.block_n;
+  d.nphase = I.n_phases; d.ksplit = I.k_splits;
+  {
+    const int ntaps0 = I.tap_gen_k ? I.tap_gen_k * I.tap_gen_k : I.n_taps[0];
+    const int total = ntaps0 * (I.k_per_tap / BLOCK_K);
+    d.it_per_split = (total + I.k_splits - 1) / I.k_splits;
+  }
+  d.epi = I.epilogue; d.oC = I.out_channels; d.ms = I.out_mul; d.split = I.out_phase_split;
+  d.leak = p->cfg.leak;
+  for (int ph = 0; ph < I.n_phases; ++ph) {
+    d.ph[ph].ntaps = I.tap_gen_k ? I.tap_gen_k * I.tap_gen_k : I.n_taps[ph];
+    d.ph[ph].mo = I.out_off_y[ph]; d.ph[ph].no = I.out_off_x[ph];
+    for (int t = 0; t < I.n_taps[ph]; ++t) {
+      const lsnf_tap& s = I.taps[ph][t];
+      d.ph[ph].taps[t] = {(int16_t)s.dy, (int16_t)s.dx, (int16_t)s.plane, 0, s.brow};
+    }
+  }
+}
+
+}  // namespace lsnf
+
+using namespace lsnf;
+
+extern "C" int lsnf_abi_version(void) { return LSNF_ABI_VERSION; }
+extern "C" const char* lsnf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
+  if (!cfg || !out) return fail(LSNF_ERR_INVALID, "null argument");
+  const lsnf_config& c = *cfg;
+  if (c.batch <= 0) return fail(LSNF_ERR_INVALID, "batch must be positive");
+  if (c.nz <= 0 || (c.nz & 1)) return fail(LSNF_ERR_INVALID, "nz must be even (model.py:383)");
+  if (c.nz % 4) return fail(LSNF_ERR_INVALID, "nz must be a multiple of 4 (128-bit latent rows)");
+  if (c.nz > 256) return fail(LSNF_ERR_INVALID, "nz > 256 is not supported");
+  if (c.f_depth <= 0 || c.f_depth > 32) return fail(LSNF_ERR_INVALID, "f_depth out of range");
+  if (c.f_width <= 0 || c.f_width > 256 || c.f_width % 4) return fail(LSNF_ERR_INVALID, "f_width must be a multiple of 4, <= 256");
+  if (c.f_permutation != 1 && c.f_permutation != 2)
+    return fail(LSNF_ERR_UNSUPPORTED, "f_flow_permutation must be 1 or 2 (model.py:372-379)");
+  if (c.f_coupling != 0 && c.f_coupling != 1)
+    return fail(LSNF_ERR_UNSUPPORTED, "f_flow_coupling must be 0 or 1 (model.py:384-387)");
+  if (c.gemm_impl != LSNF_GEMM_TCGEN05 && c.gemm_impl != LSNF_GEMM_SIMT) return fail(LSNF_ERR_INVALID, "bad gemm_impl");
+
+  lsnf_plan* p = new lsnf_plan();
+  p->cfg = c;
+  const int L = arch_layers(c, p->layers);
+  if (L < 0) { delete p; return fail(LSNF_ERR_INVALID, "unknown arch (model.py:154 raises ValueError)"); }
+  p->n_layers = L;
+  p->kp = (int)align_up(c.nz, BLOCK_K);
+  p->nzp = (int)align_up(c.nz, 128);
+  const int B = c.batch;
+
+  if (L > 0) {
+    if (c.nc <= 0 || c.nc > 4) { delete p; return fail(LSNF_ERR_INVALID, "nc must be in 1..4"); }
+    if (c.ngf <= 0) { delete p; return fail(LSNF_ERR_INVALID, "ngf must be positive"); }
+    int h = 1;
+    for (int l = 0; l < L; ++l) {
+      auto& y = p->layers[l];
+      y.hin = h;
+      y.hout = (h - 1) * y.s - 2 * y.p + y.k;
+      h = y.hout;
+      if (l < L - 1 && y.co % BLOCK_K) {
+        delete p;
+        return fail(LSNF_ERR_INVALID, "hidden generator channel counts must be multiples of 64 (raise --ngf)");
+      }
+      if (y.hin > 128) { delete p; return fail(LSNF_ERR_INVALID, "layer grid wider than 128 not supported"); }
+    }
+    p->img = h;
+  }
+
+  // ---- workspace layout ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  p->off_z = take((size_t)B * c.nz * 4);
+  p->off_gradg = take((size_t)B * c.nz * 4);
+  p->off_gradf = take((size_t)B * c.nz * 4);
+  p->off_scalars = take(256);
+  p->off_norms = take((size_t)2 * B * 4);
+  p->off_flow_out = take((size_t)B * (c.nz + 2) * 4);
+  {  // flow parameter block (floats)
+    FlowLayout& f = p->fl;
+    f.nz = c.nz; f.w = c.f_width; f.half = c.nz / 2; f.n_out = c.f_coupling ? c.nz : c.nz / 2;
+    size_t o = 0;
+    auto tk = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
+    f.an_b = tk(f.nz); f.an_e = tk(f.nz); f.an_ei = tk(f.nz);
+    f.W = tk((size_t)f.nz * f.nz); f.WT = tk((size_t)f.nz * f.nz); f.Winv = tk((size_t)f.nz * f.nz);
+    f.W1 = tk((size_t)f.half * f.w); f.W1T = tk((size_t)f.half * f.w); f.b1 = tk(f.w); f.e1 = tk(f.w);
+    f.W2 = tk((size_t)f.w * f.w); f.W2T = tk((size_t)f.w * f.w); f.b2 = tk(f.w); f.e2 = tk(f.w);
+    f.W3 = tk((size_t)f.w * f.n_out); f.W3T = tk((size_t)f.w * f.n_out); f.b3 = tk(f.n_out); f.e3 = tk(f.n_out);
+    f.perm = tk(f.nz); f.perm_inv = tk(f.nz); f.ld_const = tk(4);
+    f.step_floats = o;
+    p->off_flow = take(f.step_floats * 4 * c.f_depth);
+  }
+
+  if (L > 0) {
+    p->off_zhl = take((size_t)B * 2 * p->kp * 2);
+    for (int l = 0; l < L - 1; ++l) {
+      const auto& y = p->layers[l];
+      const size_t bytes = (size_t)B * y.hout * y.hout * 2 * y.co * 2;
+      p->off_act[l] = take(bytes);
+      p->off_gpre[l] = take(bytes);
+    }
+    for (int l = 0; l < L; ++l) p->off_bias[l] = take((size_t)p->layers[l].co * 4);
+    p->off_xhat = take((size_t)B * c.nc * p->img * p->img * 4);
+    const auto& yl = p->layers[L - 1];
+    p->off_im2col = take((size_t)B * yl.hin * yl.hin * 2 * BLOCK_K * 2);
+
+    p->stages.resize(2 * L);
+    // ---- forward stages ----
+    for (int l = 0; l < L; ++l) {
+      const auto& y = p->layers[l];
+      StageHost& st = p->stages[l];
+      lsnf_stage_info& I = st.info;
+      memset(&I, 0, sizeof(I));
+      st.layer = l; st.kind = 0; st.k = y.k; st.s = y.s; st.p = y.p; st.ci = y.ci; st.co = y.co;
+      st.first = (l == 0); st.last = (l == L - 1);
+      I.kind = 0; I.layer = l;
+      I.a_planes = 1;
+      I.k_splits = 1;
+      if (st.first) {
+        if (!(y.s == 1 && y.p == 0)) { delete p; return fail(LSNF_ERR_INVALID, "first layer must be s1 p0"); }
+        if (st.last) { delete p; return fail(LSNF_ERR_INVALID, "single-layer generator not supported"); }
+        I.grid_h = I.grid_w = 1;
+        I.k_per_tap = p->kp;
+        I.n_valid = y.k * y.k * y.co; I.n_pad = I.n_valid; I.block_n = pick_block_n(y.co);
+        I.n_phases = 1; I.n_taps[0] = 1; I.taps[0][0] = {0, 0, 0, 0};
+        I.out_mul = 1; I.out_channels = y.co; I.epilogue = EPI_ACT_HL;
+        st.a_off = p->off_zhl;
+      } else {
+        I.grid_h = I.grid_w = y.hin;
+        I.k_per_tap = y.ci;
+        if (st.last) { I.n_valid = y.co; I.n_pad = 16; I.block_n = 16; I.epilogue = EPI_OUT_TANH; }
+        else { I.n_valid = I.n_pad = y.co; I.block_n = pick_block_n(y.co); I.epilogue = EPI_ACT_HL; }
+        I.out_channels = y.co;
+        if (y.k == 4 && y.s == 2 && y.p == 1) {
+          I.n_phases = 4; I.out_mul = 2;
+          for (int ph = 0; ph < 4; ++ph) {
+            I.n_taps[ph] = up2_fwd_taps(ph >> 1, ph & 1, I.n_pad, I.taps[ph]);
+            I.out_off_y[ph] = ph >> 1; I.out_off_x[ph] = ph & 1;
+          }
+        } else if (y.k == 3 && y.s == 1 && y.p == 1) {
+          I.n_phases = 1; I.out_mul = 1; I.n_taps[0] = 9;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) I.taps[0][ky * 3 + kx] = {1 - ky, 1 - kx, 0, (ky * 3 + kx) * I.n_pad};
+        } else { delete p; return fail(LSNF_ERR_INVALID, "unsupported ConvTranspose2d geometry"); }
+        st.a_off = p->off_act[l - 1];
+      }
+      make_box(I.grid_h, I.grid_w, &I.box_b, &I.box_h, &I.box_w);
+      const int total_taps = st.first ? 1 : y.k * y.k;
+      const size_t b_rows = st.first ? (size_t)I.n_pad : (size_t)total_taps * I.n_pad;
+      I.a_h = I.grid_h; I.a_w = I.grid_w; I.tap_gen_k = 0; I.b_k = I.k_per_tap; I.b_rows = (int)b_rows;
+      st.b_bytes = b_rows * 2 * I.k_per_tap * 2;
+      st.b_off = take(st.b_bytes);
+      st.out_off = st.last ? p->off_xhat : p->off_act[l];
+      st.bias_off = p->off_bias[l];
+      I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
+      int taps_sum = 0;
+      for (int ph = 0; ph < I.n_phases; ++ph) taps_sum += I.n_taps[ph];
+      I.flops = 2LL * B * I.grid_h * I.grid_w * (long long)I.n_valid * I.k_per_tap * taps_sum;
+      if (st.first) I.flops = 2LL * B * (long long)I.n_valid * c.nz;
+      fill_dev(p, st);
+      StageDev& d = st.dev;
+      d.bias_mod = y.co;
+      if (st.last) {
+        d.nc = c.nc; d.Ho = y.hout; d.Wo = y.hout;
+      } else {
+        d.sW = 2 * y.co; d.sH = (int64_t)y.hout * d.sW; d.sB = (int64_t)y.hout * d.sH; d.sPos = d.sW; d.sP = 0;
+      }
+    }
+    // ---- data-gradient stages (executed from the last layer down to the first) ----
+    for (int l = L - 1; l >= 0; --l) {
+      const auto& y = p->layers[l];
+      StageHost& st = p->stages[L + (L - 1 - l)];
+      lsnf_stage_info& I = st.info;
+      memset(&I, 0, sizeof(I));
+      st.layer = l; st.kind = 1; st.k = y.k; st.s = y.s; st.p = y.p; st.ci = y.ci; st.co = y.co;
+      st.first = (l == 0); st.last = (l == L - 1);
+      I.kind = 1; I.layer = l; I.a_planes = 1; I.k_splits = 1;
+      I.n_phases = 1; I.out_mul = 1;
+      size_t b_rows;
+      if (st.last) {
+        if (y.k * y.k * y.co > BLOCK_K) { delete p; return fail(LSNF_ERR_INVALID, "k*k*nc must be <= 64"); }
+        I.grid_h = I.grid_w = y.hin;
+        I.k_per_tap = BLOCK_K;
+        I.n_valid = I.n_pad = y.ci; I.block_n = pick_block_n(y.ci);
+        I.n_taps[0] = 1; I.taps[0][0] = {0, 0, 0, 0};
+        st.a_off = p->off_im2col;
+        b_rows = I.n_pad;
+      } else if (st.first) {
+        I.grid_h = I.grid_w = 1;
+        I.k_per_tap = y.co;           // per output position of the first layer; taps run over the k*k positions
+        I.n_valid = c.nz; I.n_pad = p->nzp; I.block_n = 128;
+        I.n_taps[0] = 0;              // generated: tap t -> (dy, dx) = (t / k, t % k), B column offset t*co
+        st.a_off = p->off_gpre[0];
+        b_rows = I.n_pad;
+        const int kblocks = y.k * y.k * y.co / BLOCK_K;
+        const int mtiles = (B + BLOCK_M - 1) / BLOCK_M;
+        int want = std::max(1, (2 * 148 + mtiles - 1) / mtiles);
+        int per = std::max(2, (kblocks + want - 1) / want);
+        I.k_splits = (kblocks + per - 1) / per;
+        per = (kblocks + I.k_splits - 1) / I.k_splits;       // what the kernels use (it_per_split)
+        I.k_splits = (kblocks + per - 1) / per;               // every split is non-empty
+        p->ksplit_first = I.k_splits;
+      } else {
+        if (!(y.k == 4 && y.s == 2 && y.p == 1)) { delete p; return fail(LSNF_ERR_INVALID, "unsupported hidden layer geometry"); }
+        I.grid_h = I.grid_w = y.hin;
+        I.k_per_tap = y.co;
+        I.n_valid = I.n_pad = y.ci; I.block_n = pick_block_n(y.ci);
+        I.a_planes = 4;
+        I.n_taps[0] = up2_bwd_taps(I.n_pad, I.taps[0]);
+        st.a_off = p->off_gpre[l];
+        b_rows = (size_t)16 * I.n_pad;
+      }
+      make_box(I.grid_h, I.grid_w, &I.box_b, &I.box_h, &I.box_w);
+      const size_t b_k = st.first ? (size_t)y.k * y.k * y.co : (size_t)I.k_per_tap;
+      I.a_h = st.first ? y.k : I.grid_h; I.a_w = st.first ? y.k : I.grid_w;
+      I.tap_gen_k = st.first ? y.k : 0; I.b_k = (int)b_k; I.b_rows = (int)b_rows;
+      st.b_bytes = b_rows * 2 * b_k * 2;
+      st.b_off = take(st.b_bytes);
+      if (st.first) {
+        I.epilogue = EPI_PARTIAL; I.out_channels = I.n_pad;
+      } else {
+        I.epilogue = EPI_GRAD_HL; I.out_channels = y.ci;
+        // the consumer (data gradient of layer l-1) reads phase-split when it is a stride-2 layer
+        I.out_phase_split = (l - 1 > 0) ? 1 : 0;
+        st.out_off = p->off_gpre[l - 1];
+        st.mask_off = p->off_act[l - 1];
+      }
+      I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
+      I.flops = 2LL * B * I.grid_h * I.grid_w * (long long)I.n_valid *
+                (st.last ? y.k * y.k * y.co : (st.first ? (long long)y.k * y.k * y.co : 16LL * y.co));
+      fill_dev(p, st);
+      StageDev& d = st.dev;
+      if (!st.first) {
+        const int hg = I.grid_h;
+        d.sW = 2 * y.ci;
+        if (I.out_phase_split) {
+          d.sH = (int64_t)(hg / 2) * d.sW; d.sB = (int64_t)(hg / 2) * d.sH; d.sP = (int64_t)B * d.sB;
+        } else {
+          d.sH = (int64_t)hg * d.sW; d.sB = (int64_t)hg * d.sH; d.sP = 0;
+        }
+      }
+    }
+    // partial sums of the first layer's split-K data gradient
+    p->off_partial = take((size_t)p->ksplit_first * B * p->nzp * 4);
+    p->stages[2 * L - 1].out_off = p->off_partial;
+    p->stages[2 * L - 1].info.out_offset = p->off_partial;
+  }
+  p->ws_bytes = off;
+  *out = p;
+  return LSNF_OK;
+}
+
+extern "C" void lsnf_plan_destroy(lsnf_plan* plan) { delete plan; }
+
+extern "C" size_t lsnf_workspace_bytes(const lsnf_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+extern "C" int lsnf_plan_num_stages(const lsnf_plan* plan) { return plan ? (int)plan->stages.size() : 0; }
+
+extern "C" int lsnf_plan_stage_info(const lsnf_plan* plan, int32_t index, lsnf_stage_info* out) {
+  if (!plan || !out || index < 0 || index >= (int)plan->stages.size()) return fail(LSNF_ERR_INVALID, "bad stage index");
+  *out = plan->stages[index].info;
+  return LSNF_OK;
+}
+
+static PackGeom geom_of(const StageHost& st) {
+  PackGeom g;
+  g.kind = st.kind; g.first = st.first; g.last = st.last; g.k = st.k; g.ci = st.ci; g.co = st.co;
+  g.n_pad = st.info.n_pad;
+  g.ka = st.info.b_k;
+  return g;
+}
+
+extern "C" int lsnf_plan_pack_index(const lsnf_plan* plan, int32_t index, int32_t ci, int32_t co, int32_t ky,
+                                    int32_t kx, int64_t* row, int64_t* col) {
+  if (!plan || index < 0 || index >= (int)plan->stages.size() || !row || !col) return fail(LSNF_ERR_INVALID, "bad argument");
+  const StageHost& st = plan->stages[index];
+  if (ci < 0 || ci >= st.ci || co < 0 || co >= st.co || ky < 0 || ky >= st.k || kx < 0 || kx >= st.k)
+    return fail(LSNF_ERR_INVALID, "weight index out of range");
+  long long r, c;
+  pack_index(geom_of(st), ci, co, ky, kx, &r, &c);
+  *row = r; *col = c;
+  return LSNF_OK;
+}
+
+extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
+  if (!plan || !workspace) return fail(LSNF_ERR_INVALID, "null argument");
+  if (bytes < plan->ws_bytes) return fail(LSNF_ERR_INVALID, "workspace too small");
+  if ((uintptr_t)workspace % 1024) return fail(LSNF_ERR_INVALID, "workspace must be 1024-byte aligned");
+  int dev = -1;
+  LSNF_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  LSNF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(LSNF_ERR_CUDA, "this library is built for sm_100a (B200) only");
+  plan->device = dev;
+  plan->num_sms = prop.multiProcessorCount;
+  plan->ws = (char*)workspace;
+  for (auto& st : plan->stages) {
+    StageDev& d = st.dev;
+    d.a = (const __nv_bfloat16*)(plan->ws + st.a_off);
+    d.b = (const __nv_bfloat16*)(plan->ws + st.b_off);
+    d.out = plan->ws + st.out_off;
+    d.bias = st.kind == 0 ? (const float*)(plan->ws + st.bias_off) : nullptr;
+    d.mask = (st.kind == 1 && !st.first) ? (const __nv_bfloat16*)(plan->ws + st.mask_off) : nullptr;
+    if (plan->cfg.gemm_impl == LSNF_GEMM_TCGEN05) {
+      int rc = tc_encode_maps(plan, st);
+      if (rc) return rc;
+    }
+  }
+  plan->bound = true;
+  plan->g_packed = plan->f_packed = false;
+  return LSNF_OK;
+}
+
+static int need(const lsnf_plan* p, bool gen, bool flow) {
+  if (!p) return fail(LSNF_ERR_INVALID, "null plan");
+  if (!p->bound) return fail(LSNF_ERR_STATE, "lsnf_plan_bind has not been called");
+  if (gen && p->n_layers == 0) return fail(LSNF_ERR_STATE, "plan has no generator (arch = none)");
+  if (gen && !p->g_packed) return fail(LSNF_ERR_STATE, "generator weights not packed");
+  if (flow && !p->f_packed) return fail(LSNF_ERR_STATE, "flow weights not packed");
+  return 0;
+}
+
+static int run_stage(const lsnf_plan* p, const StageHost& st, cudaStream_t s) {
+  return p->cfg.gemm_impl == LSNF_GEMM_TCGEN05 ? launch_tapgemm_tc(st, s) : launch_tapgemm_simt(st, s);
+}
+
+extern "C" int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* weights, const float* const* biases,
+                                           int32_t n_layers, lsnf_stream stream) {
+  if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
+  if (n_layers != plan->n_layers || !weights || !biases) return fail(LSNF_ERR_INVALID, "layer count mismatch");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (auto& st : plan->stages) {
+    int rc = launch_pack_stage(plan, st, weights[st.layer], s);
+    if (rc) return rc;
+  }
+  for (int l = 0; l < plan->n_layers; ++l)
+    LSNF_CUDA(cudaMemcpyAsync(plan->ws + plan->off_bias[l], biases[l], (size_t)plan->layers[l].co * 4,
+                              cudaMemcpyDeviceToDevice, s));
+  plan->g_packed = true;
+  return LSNF_OK;
+}
+
+extern "C" int lsnf_pack_flow_weights(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
+                                      const int32_t* const* perm_inverse, const float* log_abs_det,
+                                      const float* const* w_inverse, lsnf_stream stream) {
+  if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
+  if (!params || (!log_abs_det && plan->cfg.f_permutation == 2)) return fail(LSNF_ERR_INVALID, "null argument");
+  if (plan->cfg.f_permutation == 1 && (!perm || !perm_inverse)) return fail(LSNF_ERR_INVALID, "permutation indices missing");
+  int rc = launch_flow_pack(plan, params, perm, perm_inverse, log_abs_det, w_inverse, (cudaStream_t)stream);
+  if (rc) return rc;
+  plan->f_packed = true;
+  plan->have_winv = (w_inverse != nullptr) || plan->cfg.f_permutation == 1;
+  return LSNF_OK;
+}
+
+static int gen_forward(lsnf_plan* p, const float* z, float* x_hat, cudaStream_t s, bool split) {
+  int rc;
+  if (split && (rc = launch_split_z(p, z, s))) return rc;
+  for (int l = 0; l < p->n_layers; ++l)
+    if ((rc = run_stage(p, p->stages[l], s))) return rc;
+  if (x_hat) {
+    const size_t bytes = (size_t)p->cfg.batch * p->cfg.nc * p->img * p->img * 4;
+    LSNF_CUDA(cudaMemcpyAsync(x_hat, p->ws + p->off_xhat, bytes, cudaMemcpyDeviceToDevice, s));
+  }
+  return LSNF_OK;
+}
+
+static int gen_dgrad_partial(lsnf_plan* p, const float* x, float sigma, cudaStream_t s) {
+  int rc;
+  if ((rc = launch_recon_grad_im2col(p, x, sigma, s))) return rc;
+  for (int i = p->n_layers; i < 2 * p->n_layers; ++i)
+    if ((rc = run_stage(p, p->stages[i], s))) return rc;
+  return LSNF_OK;
+}
+
+extern "C" int lsnf_generator_forward(lsnf_plan* plan, const float* z, float* x_hat, lsnf_stream stream) {
+  int rc = need(plan, true, false);
+  if (rc) return rc;
+  if (!z) return fail(LSNF_ERR_INVALID, "null z");
+  return gen_forward(plan, z, x_hat, (cudaStream_t)stream, true);
+}
+
+extern "C" int lsnf_generator_dgrad(lsnf_plan* plan, const float* x, float sigma, float* grad_z, lsnf_stream stream) {
+  int rc = need(plan, true, false);
+  if (rc) return rc;
+  if (!x || !grad_z || !(sigma > 0.f)) return fail(LSNF_ERR_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = gen_dgrad_partial(plan, x, sigma, s))) return rc;
+  return launch_reduce_partial(plan, grad_z, s);
+}
+
+extern "C" int lsnf_flow_forward(lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
+                                 float* grad_z, lsnf_stream stream) {
+  int rc = need(plan, false, true);
+  if (rc) return rc;
+  if (!z) return fail(LSNF_ERR_INVALID, "null z");
+  return launch_flow_forward(plan, z, z_out, logdet, logp, grad_z, (cudaStream_t)stream);
+}
+
+extern "C" int lsnf_flow_inverse(lsnf_plan* plan, const float* eps, float* z, float* neg_objective, lsnf_stream stream) {
+  int rc = need(plan, false, true);
+  if (rc) return rc;
+  if (!eps || !z) return fail(LSNF_ERR_INVALID, "null argument");
+  if (!plan->have_winv) return fail(LSNF_ERR_STATE, "flow weights were packed without w_inverse");
+  return launch_flow_inverse(plan, eps, z, neg_objective, (cudaStream_t)stream);
+}
+
+extern "C" int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad_g, const float* grad_f,
+                                    float step_size, const float* eps, int32_t with_noise, uint64_t seed,
+                                    uint64_t sample_offset, uint32_t step, float* gnorms, lsnf_stream stream) {
+  if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
+  if (!z || !grad_g || !grad_f) return fail(LSNF_ERR_INVALID, "null argument");
+  return launch_update(plan, z, grad_g, nullptr, 0, grad_f, step_size, eps, with_noise, seed, sample_offset, step,
+                       nullptr, gnorms, 0, (cudaStream_t)stream);
+}
+
+extern "C" int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps) {
+  if (!plan) return 0;
+  // per step: L forward + im2col + L data-gradient + flow + update; once: split_z
+  return 1 + steps * (2 * plan->n_layers + 3);
+}
+
+extern "C" int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t steps, float step_size,
+                                 float sigma, int32_t with_noise, const float* eps, uint64_t seed,
+                                 uint64_t sample_offset, float* z_out, float* gnorms, lsnf_stream stream) {
+  int rc = need(plan, true, true);
+  if (rc) return rc;
+  if (!z0 || !x || !z_out || steps < 0 || !(sigma > 0.f)) return fail(LSNF_ERR_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const lsnf_config& c = plan->cfg;
+  float* z = (float*)(plan->ws + plan->off_z);
+  float* gf = (float*)(plan->ws + plan->off_gradf);
+  const float* partial = (const float*)(plan->ws + plan->off_partial);
+  const size_t zbytes = (size_t)c.batch * c.nz * 4;
+  LSNF_CUDA(cudaMemcpyAsync(z, z0, zbytes, cudaMemcpyDeviceToDevice, s));
+  if ((rc = launch_split_z(plan, z, s))) return rc;
+  for (int t = 0; t < steps; ++t) {
+    if ((rc = gen_forward(plan, z, nullptr, s, false))) return rc;
+    if ((rc = gen_dgrad_partial(plan, x, sigma, s))) return rc;
+    if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, s))) return rc;
+    const float* e = eps ? eps + (size_t)t * c.batch * c.nz : nullptr;
+    if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gf, step_size, e, with_noise, seed,
+                            sample_offset, (uint32_t)t, nullptr, t == steps - 1 ? gnorms : nullptr, 1, s)))
+      return rc;
+  }
+  LSNF_CUDA(cudaMemcpyAsync(z_out, z, zbytes, cudaMemcpyDeviceToDevice, s));
+  return LSNF_OK;
+}

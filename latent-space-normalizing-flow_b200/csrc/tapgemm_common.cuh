@@ -1,0 +1,106 @@
+// Tile -> row-grid mapping and the fused epilogues shared by the tcgen05 tap-GEMM and its SIMT twin.
+#pragma once
+#include "lsnf_internal.cuh"
+
+namespace lsnf {
+
+struct RowCtx {
+  int b, m, n;  // sample and position in the stage's row grid
+  bool valid;
+};
+
+__device__ __forceinline__ void tile_origin(const StageDev& st, int mtile, int& b0, int& h0, int& w0) {
+  const int wt = mtile % st.tiles_w, ht = (mtile / st.tiles_w) % st.tiles_h, bt = mtile / (st.tiles_w * st.tiles_h);
+  b0 = bt * st.bB; h0 = ht * st.bH; w0 = wt * st.bW;
+}
+
+__device__ __forceinline__ RowCtx tile_row(const StageDev& st, int mtile, int r) {
+  int b0, h0, w0;
+  tile_origin(st, mtile, b0, h0, w0);
+  RowCtx rc;
+  rc.n = w0 + r % st.bW;
+  rc.m = h0 + (r / st.bW) % st.bH;
+  rc.b = b0 + r / (st.bW * st.bH);
+  rc.valid = rc.b < st.B;
+  return rc;
+}
+
+__device__ __forceinline__ void split_pack(const float* v, int n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  for (int j = 0; j < n; ++j) {
+    hi[j] = __float2bfloat16_rn(v[j]);
+    lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+  }
+}
+
+// Applies the stage's epilogue to NV consecutive accumulator columns [col, col+NV) of one row and stores them.
+// NV is 4 or 8; col % NV == 0.  Reference semantics: bias + LeakyReLU / Tanh of model.py:56-151, and for the
+// data gradient the LeakyReLU derivative autograd applies (train.py:314).
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, int split_idx, const RowCtx& rc,
+                                               int col, const float* acc) {
+  if (!rc.valid || col >= st.n_pad) return;
+  using Vec = typename std::conditional<NV == 8, uint4, uint2>::type;
+  if (st.epi == EPI_ACT_HL) {
+    const int pos = col / st.oC, cb = col % st.oC;
+    const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float t = acc[j] + __ldg(st.bias + (col + j) % st.bias_mod);
+      v[j] = t > 0.f ? t : t * st.leak;
+    }
+    __align__(16) __nv_bfloat16 hi[NV], lo[NV];
+    split_pack(v, NV, hi, lo);
+    __nv_bfloat16* o = (__nv_bfloat16*)st.out + (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW +
+                       (size_t)pos * st.sPos + cb;
+    *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
+    *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
+  } else if (st.epi == EPI_OUT_TANH) {
+    const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
+    float* o = (float*)st.out;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = col + j;
+      if (c < st.nc) o[(((size_t)rc.b * st.nc + c) * st.Ho + mo) * st.Wo + no] = tanhf(acc[j] + __ldg(st.bias + c));
+    }
+  } else if (st.epi == EPI_GRAD_HL) {
+    const __nv_bfloat16* mk = st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + col;
+    __align__(16) __nv_bfloat16 mv[NV];
+    *reinterpret_cast<Vec*>(mv) = *reinterpret_cast<const Vec*>(mk);
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = __bfloat162float(mv[j]) > 0.f ? acc[j] : acc[j] * st.leak;
+    __align__(16) __nv_bfloat16 hi[NV], lo[NV];
+    split_pack(v, NV, hi, lo);
+    size_t off;
+    if (st.split)
+      off = (size_t)((rc.m & 1) * 2 + (rc.n & 1)) * st.sP + (size_t)rc.b * st.sB + (size_t)(rc.m >> 1) * st.sH +
+            (size_t)(rc.n >> 1) * st.sW;
+    else
+      off = (size_t)rc.b * st.sB + (size_t)rc.m * st.sH + (size_t)rc.n * st.sW;
+    __nv_bfloat16* o = (__nv_bfloat16*)st.out + off + col;
+    *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
+    *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
+  } else {  // EPI_PARTIAL
+    float* o = (float*)st.out + ((size_t)split_idx * st.B + rc.b) * st.n_pad + col;
+    if (NV == 8) {
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  }
+}
+
+// tap of iteration `t` of a phase: table entry, or generated for the first layer's data gradient
+__device__ __forceinline__ void get_tap(const StageDev& st, int phase, int t, int& dy, int& dx, int& plane,
+                                        int& brow, int& bcol) {
+  if (st.tap_gen) {
+    dy = t / st.tap_gen; dx = t % st.tap_gen; plane = 0; brow = 0; bcol = t * st.Ka;
+  } else {
+    const TapDev& tp = st.ph[phase].taps[t];
+    dy = tp.dy; dx = tp.dx; plane = tp.plane; brow = tp.brow; bcol = 0;
+  }
+}
+
+}  // namespace lsnf

@@ -1,0 +1,315 @@
+// tcgen05 / TMEM / TMA tap-GEMM for sm_100a: the generator's transposed convolutions (forward, train.py:312)
+// and their data gradients (train.py:314) as implicit GEMMs.
+//
+//   D[row, n] = sum_{tap} sum_{k} A[plane_tap][b][m + dy_tap][n + dx_tap][k] * W[brow_tap + n][k]
+//
+// * A rows are 128 grid positions (b, m, n) fetched by ONE 5-D TMA box per tap and K block; the (dy, dx) shift
+//   moves the box, and TMA's out-of-bounds zero fill supplies the convolution padding and the ragged batch.
+// * Operands are bf16 hi|lo pairs (value = hi + lo); each K step issues three tcgen05.mma (hi*hi, hi*lo, lo*hi)
+//   into one fp32 TMEM accumulator -- the 3-pass split that keeps z_T within the 1e-4 parity budget.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> bias/activation/derivative -> bf16 hi|lo or fp32 stores).
+#include <type_traits>
+
+#include "tapgemm_common.cuh"
+
+namespace lsnf {
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB per hi or lo half
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major), encoded 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t umma_idesc() {
+  // c_format F32 (bits 4-5 = 1), a/b format BF16 (bits 7-9, 10-12 = 1), K-major A and B, N>>3 at 17, M>>4 at 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ StageDev st) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = tiles + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier block: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
+  uint8_t* gen_base = smem_raw + (tiles - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(gen_base + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtile = blockIdx.x, n0 = blockIdx.y * BN;
+  const int phase = blockIdx.z / st.ksplit, split = blockIdx.z % st.ksplit;
+  const int kblocks = st.Ka / BLOCK_K;
+  const int total = st.ph[phase].ntaps * kblocks;
+  const int it0 = split * st.it_per_split, it1 = min(total, it0 + st.it_per_split);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int b0, h0, w0;
+      tile_origin(st, mtile, b0, h0, w0);
+      for (int it = it0; it < it1; ++it) {
+        const int i = it - it0, s = i % Cfg::STAGES;
+        const uint32_t par = (uint32_t)((i / Cfg::STAGES) & 1);
+        mbar_wait(empty_bar(s), par ^ 1u);
+        const int t = it / kblocks, kb = it % kblocks;
+        int dy, dx, plane, brow, bcol;
+        get_tap(st, phase, t, dy, dx, plane, brow, bcol);
+        const uint32_t sa = tiles + s * Cfg::STAGE_BYTES;
+        const uint32_t sb = sa + 2 * A_TILE_BYTES;
+        mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        tma_load_5d(sa, &tmA, full_bar(s), kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
+        tma_load_5d(sa + A_TILE_BYTES, &tmA, full_bar(s), st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
+        tma_load_2d(sb, &tmB, full_bar(s), bcol + kb * BLOCK_K, brow + n0);
+        tma_load_2d(sb + Cfg::B_TILE_BYTES, &tmB, full_bar(s), st.b_k + bcol + kb * BLOCK_K, brow + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc<BN>();
+      for (int it = it0; it < it1; ++it) {
+        const int i = it - it0, s = i % Cfg::STAGES;
+        const uint32_t par = (uint32_t)((i / Cfg::STAGES) & 1);
+        mbar_wait(full_bar(s), par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = tiles + s * Cfg::STAGE_BYTES;
+        const uint32_t sb = sa + 2 * A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+          const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + Cfg::B_TILE_BYTES + k * 32);
+          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));  // frees the smem slot once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const RowCtx rc = tile_row(st, mtile, r);
+    if (it1 > it0) mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+      uint32_t v[CH];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
+      if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float f[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) f[j] = (it1 > it0) ? __uint_as_float(v[j]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < CH; j += 8) epilogue_store<8>(st, phase, split, rc, n0 + c + j, f + j);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host: tensor-map encoding (driver entry point fetched at run time; the library does not link libcuda)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return LSNF_ERR_CUDA; }
+  const StageDev& d = sh.dev;
+  {
+    const cuuint64_t row = (cuuint64_t)2 * d.Ka * 2;  // bytes per position (hi|lo)
+    cuuint64_t dims[5] = {(cuuint64_t)2 * d.Ka, (cuuint64_t)d.aW, (cuuint64_t)d.aH, (cuuint64_t)d.B, (cuuint64_t)d.aP};
+    cuuint64_t strides[4] = {row, row * d.aW, row * d.aW * d.aH, row * d.aW * d.aH * d.B};
+    cuuint32_t box[5] = {BLOCK_K, (cuuint32_t)d.bW, (cuuint32_t)d.bH, (cuuint32_t)d.bB, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&sh.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)d.a, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)r) + " for stage layer " +
+                std::to_string(sh.layer) + " kind " + std::to_string(sh.kind));
+      return LSNF_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)2 * d.b_k, (cuuint64_t)d.b_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)2 * d.b_k * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)d.block_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&sh.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.b, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r) + " for stage layer " +
+                std::to_string(sh.layer) + " kind " + std::to_string(sh.kind));
+      return LSNF_ERR_CUDA;
+    }
+  }
+  sh.maps_ready = true;
+  return LSNF_OK;
+}
+
+template <int BN>
+static int launch_bn(const StageHost& sh, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const StageDev& st = sh.dev;
+  dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, st.nphase * st.ksplit);
+  tapgemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(sh.tmA, sh.tmB, st);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+int launch_tapgemm_tc(const StageHost& sh, cudaStream_t s) {
+  if (!sh.maps_ready) { set_error("tensor maps not encoded"); return LSNF_ERR_STATE; }
+  switch (sh.dev.block_n) {
+    case 256: return launch_bn<256>(sh, s);
+    case 128: return launch_bn<128>(sh, s);
+    case 64: return launch_bn<64>(sh, s);
+    case 16: return launch_bn<16>(sh, s);
+    default: set_error("unsupported N tile"); return LSNF_ERR_INVALID;
+  }
+}
+
+}  // namespace lsnf

@@ -1,0 +1,102 @@
+"""``sample_langevin_post_z_with_flow`` -- the reference closure (train.py:307-335; test variant :602-634) as one
+call into the CUDA library.  No autograd, no per-step Python: the whole ``g_l_steps`` loop is enqueued by
+``lsnf_langevin_run`` on the caller's current stream."""
+from __future__ import annotations
+
+import itertools
+from typing import Optional
+
+import torch
+
+from .model import _get, _netF, _netG
+from .plan import get_plan
+
+_call_counter = itertools.count()
+
+
+class AttrDict(dict):
+    """Same access pattern as the reference's ``AttrDict`` (train.py:743-746)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+def make_args(**overrides) -> AttrDict:
+    """Defaults of train.py:37-99 for every flag the hot path reads; ``overrides`` use the CLI flag names."""
+    a = AttrDict(test_mode=False, seed=1, dataset="svhn", img_size=32, batch_size=100, nz=100, nc=3, ngf=64,
+                 g_llhd_sigma=0.3, g_activation="lrelu", g_activation_leak=0.2, g_l_steps=20, g_l_step_size=0.1,
+                 g_l_with_noise=True, g_batchnorm=False, f_n_levels=1, f_depth=5, f_flow_permutation=2, f_width=64,
+                 f_flow_coupling=1)
+    unknown = set(overrides) - set(a) - {"device", "job_id", "status"}
+    if unknown:
+        raise TypeError(f"unknown argument(s): {sorted(unknown)}")
+    a.update(overrides)
+    return a
+
+
+def langevin_plan(netG: _netG, netF: _netF, batch: int, device):
+    return get_plan(arch=netG.dataset, batch=batch, nz=netG.nz, ngf=netG.ngf, nc=netG.nc, f_depth=netF.f_depth,
+                    f_width=netF.f_width, f_permutation=netF.f_permutation, f_coupling=netF.f_coupling,
+                    leak=netG.leak, device=device, gemm_impl=netG.gemm_impl)
+
+
+def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbose: bool = False, *,
+                                     eps: Optional[torch.Tensor] = None, steps: Optional[int] = None,
+                                     with_noise: Optional[bool] = None, seed: Optional[int] = None,
+                                     sample_offset: int = 0):
+    """z [B,nz,1,1], x [B,nc,H,W] -> (z_k [B,nz,1,1], mean_b|grad_g|, mean_b|grad_f|) as train.py:335 returns them.
+
+    ``args`` supplies g_l_steps, g_l_step_size, g_l_with_noise, g_llhd_sigma (train.py:311-326).  ``eps``
+    [steps,B,nz,1,1] injects the noise (parity runs); otherwise noise is drawn in-kernel from Philox keyed by
+    (seed, sample_offset + b, step), so a sharded batch reproduces the unsharded result bit for bit.  The
+    diagnostics use the real batch size (the reference's ``view(args.batch_size, -1)`` breaks on a ragged batch).
+    """
+    if not isinstance(netG, _netG) or not isinstance(netF, _netF):
+        raise TypeError("netG / netF must be lsnf_b200._netG / _netF instances")
+    if not (z.is_cuda and x.is_cuda):
+        raise RuntimeError("sample_langevin_post_z_with_flow needs CUDA tensors: there is no CPU fallback")
+    B = z.shape[0]
+    if netF.nz != netG.nz:
+        raise ValueError("netG and netF disagree on nz")
+    T = int(_get(args, "g_l_steps", 20) if steps is None else steps)
+    s = float(_get(args, "g_l_step_size", 0.1))
+    sigma = float(_get(args, "g_llhd_sigma", 0.3))
+    noise = bool(_get(args, "g_l_with_noise", True)) if with_noise is None else bool(with_noise)
+    z2 = z.detach().reshape(B, netG.nz).contiguous().float()
+    xx = x.detach().contiguous().float()
+    e = None
+    if eps is not None:
+        e = eps.detach().reshape(T, B, netG.nz).contiguous().float()
+    if seed is None:
+        seed = (int(_get(args, "seed", 1)) << 32) ^ next(_call_counter)
+    plan = langevin_plan(netG, netF, B, z2.device)
+    plan.ensure_generator(netG)
+    plan.ensure_flow(netF)
+    out, norms = plan.langevin_run(z2, xx, T, s, sigma, with_noise=noise, eps=e, seed=seed,
+                                   sample_offset=sample_offset)
+    if verbose:
+        print("Langevin posterior: z_grad_g_grad_norm={:8.3f}, z_grad_f_grad_norm={:8.3f}".format(
+            norms[0].item(), norms[1].item()))
+    return out.reshape(B, netG.nz, 1, 1), norms[0], norms[1]
+
+
+def make_sampler(args, test_mode: bool = False):
+    """Closure with the reference's exact signature ``f(z, x, netG, netF, verbose=False)``.
+
+    ``test_mode=True`` reproduces the test variant: ``g_l_steps * 20`` iterations and no noise
+    (train.py:606, :623-625)."""
+    def sampler(z, x, netG, netF, verbose=False):
+        if test_mode:
+            return sample_langevin_post_z_with_flow(z, x, netG, netF, args, verbose,
+                                                    steps=int(_get(args, "g_l_steps", 20)) * 20, with_noise=False)
+        return sample_langevin_post_z_with_flow(z, x, netG, netF, args, verbose)
+    return sampler
+
+
+def sample_x(netG: _netG, netF: _netF, n: int, device, generator: Optional[torch.Generator] = None):
+    """Prior sampling of train.py:567-576: eps ~ N(0,I) -> z = F^-1(eps) -> x = G(z), mapped to [0,1]."""
+    eps = torch.randn(n, netG.nz, device=device, generator=generator)
+    z, _ = netF.inverse(eps)
+    xs = netG.generate(z)
+    return ((xs + 1.0) / 2.0).clamp(min=0.0, max=1.0)
