@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the Langevin posterior-inference path (BASELINE.json metric: latent-steps/s, CIFAR-10 config).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cifar10|svhn|...]
+
+One "step" = one call of sample_langevin_post_z_with_flow (train.py:307-335) over one batch of synthetic input:
+T = g_l_steps Langevin iterations on B latents per GPU.  value = N * B * T * K / time, inputs resident in HBM, timed
+with CUDA events, max over ranks.  `e2e` is the same metric through the public Python API with pinned HOST buffers,
+host<->device copies inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # BASELINE.json configs (README commands of the reference)
+    "svhn": dict(dataset="svhn", nz=100, ngf=64, f_width=64, T=20, sigma=0.3, B=100, img=32),
+    "cifar10": dict(dataset="cifar10", nz=128, ngf=128, f_width=64, T=40, sigma=0.3, B=100, img=32),
+    "celeba_crop": dict(dataset="celeba_crop", nz=100, ngf=128, f_width=64, T=20, sigma=0.3, B=100, img=64),
+    "celeba_hq256": dict(dataset="celeba_hq256", nz=100, ngf=128, f_width=128, T=20, sigma=1.0, B=8, img=256),
+}
+ROOFLINE_LATENT_STEPS = {"svhn": 5.98e6, "cifar10": 347e3, "celeba_crop": 971e3, "celeba_hq256": 112e3}
+
+
+def exact_layer_flops(layers):
+    """Per-sample FLOPs (2 x MACs whose taps land inside the output) of each ConvTranspose2d -- SURVEY.md 8a table."""
+    out, hin = [], 1
+    for (ci, co, k, s, p) in layers:
+        hout = (hin - 1) * s - 2 * p + k
+        cnt1d = sum(1 for i in range(hin) for kk in range(k) if 0 <= i * s - p + kk < hout)
+        out.append(2.0 * cnt1d * cnt1d * ci * co)
+        hin = hout
+    return out
+
+
+def flow_flops(nz, w, depth=5):
+    return 2.0 * depth * 2.0 * (nz * nz + nz // 2 * w + w * w + w * nz)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"],
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def build_models(w, device):
+    import lsnf_b200
+    from lsnf_b200 import synth
+    args = lsnf_b200.make_args(dataset=w["dataset"], nz=w["nz"], ngf=w["ngf"], f_width=w["f_width"],
+                               g_llhd_sigma=w["sigma"], g_l_steps=w["T"], batch_size=w["B"])
+    netG = lsnf_b200._netG(args).to(device).eval()
+    netF = lsnf_b200._netF(args, nz=w["nz"]).to(device).eval()
+    gsd = synth.generator_state(w["dataset"], w["nz"], w["ngf"], 3, seed=1)
+    fsd = synth.flow_state(w["nz"], w["f_width"], 5, 1, 2, seed=1)
+    netG.load_state_dict({k: torch.from_numpy(v) for k, v in gsd.items()})
+    netF.load_state_dict({k: torch.from_numpy(v) for k, v in fsd.items()})
+    return args, netG, netF, gsd, fsd
+
+
+def cpu_oracle_rate(w, gsd, fsd, langevin_steps, repeats=1, threads=None):
+    """latent-steps/s of the CPU oracle (restatement of the reference's torch path) on the host cores."""
+    from oracle import refpath
+    from lsnf_b200 import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gp = {k: torch.from_numpy(v) for k, v in gsd.items()}
+    fp = {k: torch.from_numpy(v) for k, v in fsd.items()}
+    layers = refpath.generator_layers(w["dataset"], w["nz"], w["ngf"])
+    x, z0, eps = synth.inputs(w["B"], w["nz"], 3, w["img"], langevin_steps, seed=1)
+    x, z0, eps = torch.from_numpy(x), torch.from_numpy(z0), torch.from_numpy(eps)
+    refpath.langevin(z0, x, gp, fp, layers, depth=5, steps=1, step_size=0.1, sigma=w["sigma"], eps=eps)  # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        refpath.langevin(z0, x, gp, fp, layers, depth=5, steps=langevin_steps, step_size=0.1, sigma=w["sigma"], eps=eps)
+        best = min(best, time.perf_counter() - t0)
+    return w["B"] * langevin_steps / best, best, threads
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(a, w, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure
+    Python/torch and does not travel to the GPU box) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from lsnf_b200 import synth
+    gsd = synth.generator_state(w["dataset"], w["nz"], w["ngf"], 3, seed=1)
+    fsd = synth.flow_state(w["nz"], w["f_width"], 5, 1, 2, seed=1)
+    sample_T = {"svhn": 4, "cifar10": 1, "celeba_crop": 1, "celeba_hq256": 1}[a.workload]
+    for _ in range(max(a.warmup, 1) - 1):
+        cpu_oracle_rate(w, gsd, fsd, 1)
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(a.steps):
+        rate, dt, threads = cpu_oracle_rate(w, gsd, fsd, sample_T)
+        total += dt
+    value = w["B"] * sample_T * a.steps / total
+    sample = f"{sample_T} Langevin iteration(s) of B={w['B']} per step (per-iteration cost does not depend on T)"
+    line = {"impl": "reference", "metric": "langevin_latent_steps_per_sec", "value": value, "unit": "latent-steps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": a.workload, **{k: w[k] for k in ("dataset", "nz", "ngf", "f_width", "T", "B")},
+                       "cpu": cpu_model()},
+            "cpu_baseline": {"value": value, "unit": "latent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cifar10", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the reference's 100)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-table", default=None, help="write the per-stage timing table (json) here")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.batch:
+        w["B"] = a.batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, w, rank)
+        return
+    if a.warmup < 3:
+        a.warmup = 3
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    import torch.distributed as dist
+    import lsnf_b200
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args, netG, netF, gsd, fsd = build_models(w, dev)
+    from lsnf_b200 import synth
+    B, T, nz = w["B"], w["T"], w["nz"]
+    x_np, z0_np, _ = synth.inputs(B, nz, 3, w["img"], 1, seed=1 + rank)
+    x, z0 = torch.from_numpy(x_np).to(dev), torch.from_numpy(z0_np).to(dev).reshape(B, nz).contiguous()
+    plan = lsnf_b200.langevin_plan(netG, netF, B, dev)
+    plan.ensure_generator(netG)
+    plan.ensure_flow(netF)
+    out = torch.empty_like(z0)
+    norms = torch.zeros(2, device=dev)
+    sample_offset = rank * B
+
+    def step(i):
+        plan.langevin_run(z0, x, T, 0.1, w["sigma"], with_noise=True, eps=None, seed=1234 + i,
+                          sample_offset=sample_offset, out=out, norms=norms)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(a.warmup + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(out).all(), "non-finite latents"
+    value = world * B * T * a.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API: pinned host buffers, H2D + D2H inside the timed region ----
+    z0_h = torch.from_numpy(z0_np).pin_memory()
+    x_h = torch.from_numpy(x_np).pin_memory()
+    z_res_h = torch.empty(B, nz, 1, 1).pin_memory()
+    n_res_h = torch.empty(2).pin_memory()
+
+    def e2e_step(i):
+        zd = z0_h.to(dev, non_blocking=True)
+        xd = x_h.to(dev, non_blocking=True)
+        zk, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(zd, xd, netG, netF, args, seed=99 + i,
+                                                                sample_offset=sample_offset)
+        z_res_h.copy_(zk, non_blocking=True)
+        n_res_h.copy_(torch.stack([gn, fn]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the result on the host
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i + 1)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * a.steps / float(e2e_s.item())
+    h2d = z0_h.numel() * 4 + x_h.numel() * 4
+    d2h = z_res_h.numel() * 4 + 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: per-stage CUDA-event timing through lsnf_plan_run_stage ----
+    pk = peaks()
+    layers = synth.generator_layers(w["dataset"], nz, w["ngf"])
+    exact = exact_layer_flops(layers)
+    stages = plan.stages()
+    reps = 10
+    table = []
+    for idx, info in enumerate(stages):
+        for _ in range(2):
+            plan.run_stage(idx)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            plan.run_stage(idx)
+        s1.record()
+        torch.cuda.synchronize()
+        us = s0.elapsed_time(s1) * 1e3 / reps
+        alg = exact[info.layer] * B
+        table.append(dict(stage=idx, kind="fwd" if info.kind == 0 else "dgrad", layer=info.layer, us=us,
+                          alg_gflop=alg / 1e9, nominal_gflop=info.flops / 1e9, tflops_alg=alg / us / 1e6,
+                          block_n=info.block_n, k_splits=info.k_splits))
+    gemm_us = sum(t["us"] for t in table)
+    dom = max(table, key=lambda t: t["us"])
+    step_us = ms_total * 1e3 / a.steps / T   # one Langevin iteration
+    roofline = {"bound": "tensor", "achieved": dom["tflops_alg"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": dom["tflops_alg"] / pk["tflops"], "traffic": None,
+                "kernel": f"tapgemm_tc_kernel<{dom['block_n']}> stage {dom['stage']} ({dom['kind']} layer {dom['layer']})",
+                "kernel_us": dom["us"], "alg_gflop_per_launch": dom["alg_gflop"],
+                "peak_source": pk["src"] + ", burst bf16 (kernel timed alone)",
+                "mma": "tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulate), 3 passes (hi*hi + hi*lo + lo*hi); "
+                       "algorithmic FLOPs count one pass",
+                "share_of_iteration": dom["us"] / step_us, "all_gemm_stages_us": gemm_us, "iteration_us": step_us}
+    if a.stage_table:
+        json.dump(table, open(a.stage_table, "w"), indent=1)
+
+    cpu_b = None
+    if not a.no_cpu_baseline:
+        cpu_T = {"svhn": 8, "cifar10": 3, "celeba_crop": 4, "celeba_hq256": 3}[a.workload]
+        rate, dt, threads = cpu_oracle_rate(w, gsd, fsd, cpu_T)
+        cpu_b = {"value": rate, "unit": "latent-steps/s", "cores": threads, "kind": "port",
+                 "sample": f"{cpu_T} Langevin iterations of the same B={B} workload in {dt:.1f} s on {cpu_model()} "
+                           f"(oracle/refpath.py, torch CPU fp32)"}
+
+    alg_per_ls = 2 * sum(exact) + flow_flops(nz, w["f_width"])
+    line = {
+        "metric": "langevin_latent_steps_per_sec", "value": value, "unit": "latent-steps/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split/f32-accumulate", "data": "synthetic",
+        "config": {"workload": a.workload, "dataset": w["dataset"], "nz": nz, "ngf": w["ngf"], "f_width": w["f_width"],
+                   "g_l_steps": T, "batch_per_gpu": B, "g_llhd_sigma": w["sigma"], "noise": "in-kernel Philox4x32-10",
+                   "l2": f"no flush: per-call working set {plan.ws_bytes / 1e6:.0f} MB > 126 MB L2",
+                   "alg_gflop_per_latent_step": alg_per_ls / 1e9,
+                   "frac_of_tensor_roofline": value / world / (pk["tflops_sustained"] * 1e12 / alg_per_ls),
+                   "roofline_denominator": f"{pk['tflops_sustained']} TFLOP/s bf16 sustained, {pk['src']}"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": a.steps * plan.launch_count(T),
+        "roofline": roofline,
+        "cpu_baseline": cpu_b,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

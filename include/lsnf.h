@@ -134,6 +134,9 @@ int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad_g, const f
 int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t steps, float step_size,
                       float sigma, int32_t with_noise, const float* eps, uint64_t seed, uint64_t sample_offset,
                       float* z_out, float* gnorms, lsnf_stream stream);
+/* Launches generator stage `index` alone (0..L-1 forward, L..2L-1 data gradient) on the buffers currently in the
+ * workspace.  Profiling / test hook: bench.py times the dominant tap-GEMM with CUDA events through it. */
+int lsnf_plan_run_stage(lsnf_plan* plan, int32_t index, lsnf_stream stream);
 /* how many kernels one lsnf_langevin_run of `steps` iterations launches (for bench.py's gpu_launches). */
 int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps);
 
@@ -162,13 +165,14 @@ typedef struct lsnf_stage_info {
   int32_t out_off_y[LSNF_MAX_PHASES], out_off_x[LSNF_MAX_PHASES];
   int32_t out_phase_split; /* output written in phase-split layout */
   int32_t out_channels;  /* channels per output position (n_pad may span several positions) */
-  int32_t epilogue;      /* 0 bias+lrelu -> bf16 hi/lo, 1 bias+tanh -> fp32 NCHW, 2 *lrelu' -> bf16 hi/lo, 3 fp32 split-K partial */
+  int32_t epilogue;      /* 0 bias+lrelu -> bf16 hi/lo, 1 bias+tanh -> fp32 NCHW, 2 *lrelu' -> bf16 hi/lo, 3 raw fp32 rows (split-K partials / per-tap products of the last forward layer) */
   int32_t k_splits;
   int32_t a_planes;      /* planes of the A operand (4 when phase-split) */
   int32_t a_h, a_w;      /* spatial extent of the A operand (== grid except for the first layer's data gradient) */
   int32_t tap_gen_k;     /* != 0: taps are generated, tap t = (dy, dx) = (t / k, t % k), weight column offset t*k_per_tap */
   int32_t b_k;           /* columns of the hi half of the packed weight matrix (lo half follows) */
   int32_t b_rows;        /* rows of the packed weight matrix */
+  int32_t operand_fp16;  /* operands are fp16 hi|lo (forward stages) rather than bf16 hi|lo (data-gradient stages) */
   int64_t a_offset, b_offset, out_offset; /* byte offsets into the workspace */
   int64_t flops;         /* 2*M*N*K over all phases and taps (nominal, padded taps included) */
 } lsnf_stage_info;

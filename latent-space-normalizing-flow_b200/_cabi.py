@@ -37,7 +37,7 @@ class StageInfo(C.Structure):
                 ("out_off_x", C.c_int32 * LSNF_MAX_PHASES), ("out_phase_split", C.c_int32),
                 ("out_channels", C.c_int32), ("epilogue", C.c_int32), ("k_splits", C.c_int32),
                 ("a_planes", C.c_int32), ("a_h", C.c_int32), ("a_w", C.c_int32), ("tap_gen_k", C.c_int32),
-                ("b_k", C.c_int32), ("b_rows", C.c_int32),
+                ("b_k", C.c_int32), ("b_rows", C.c_int32), ("operand_fp16", C.c_int32),
                 ("a_offset", C.c_int64), ("b_offset", C.c_int64), ("out_offset", C.c_int64), ("flops", C.c_int64)]
 
 
@@ -62,6 +62,7 @@ EXPORTS = {
                                        C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "lsnf_langevin_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsnf_plan_run_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "lsnf_langevin_launch_count": (C.c_int, [C.c_void_p, C.c_int32]),
     "lsnf_plan_num_stages": (C.c_int, [C.c_void_p]),
     "lsnf_plan_stage_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StageInfo)]),

@@ -13,8 +13,9 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 // weight packing: ConvTranspose2d weight [ci][co][k][k] fp32 -> K-major bf16 hi|lo operand of one stage
 // (model.py:57-149 weights; layouts documented at pack_index in lsnf_internal.cuh)
 // ---------------------------------------------------------------------------------------------------
-__global__ void pack_stage_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackGeom g,
-                                  int rows, int nz_valid) {
+__global__ void pack_stage_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, PackGeom g, int rows,
+                                  int nz_valid, int fp16, const float* __restrict__ scale) {
+  const float sc = scale ? *scale : 1.f;
   const long long total = (long long)rows * g.ka;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -22,7 +23,7 @@ __global__ void pack_stage_kernel(const float* __restrict__ w, __nv_bfloat16* __
     int ci = -1, co = -1, tap = -1;
     if (g.kind == 0) {
       ci = col;
-      if (g.first) { tap = row / g.co; co = row % g.co; }
+      if (g.first || g.last) { tap = row / g.co; co = row % g.co; }
       else { tap = row / g.n_pad; co = row % g.n_pad; }
     } else if (g.first || g.last) {
       ci = row; tap = col / g.co; co = col % g.co;
@@ -31,9 +32,9 @@ __global__ void pack_stage_kernel(const float* __restrict__ w, __nv_bfloat16* __
     }
     float v = 0.f;
     if (ci < g.ci && co < g.co && tap < g.k * g.k && ci < nz_valid)
-      v = w[((long long)ci * g.co + co) * g.k * g.k + tap];
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
+      v = w[((long long)ci * g.co + co) * g.k * g.k + tap] * sc;
+    uint16_t hi, lo;
+    split16(v, fp16 != 0, hi, lo);
     out[(long long)row * 2 * g.ka + col] = hi;
     out[(long long)row * 2 * g.ka + g.ka + col] = lo;
   }
@@ -47,28 +48,110 @@ int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w
   const long long total = (long long)rows * g.ka;
   const int threads = 256;
   const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
-  pack_stage_kernel<<<blocks, threads, 0, s>>>(w, (__nv_bfloat16*)(plan->ws + st.b_off), g, rows, st.ci);
+  const float* scale = st.kind == 0 ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 4) : nullptr;
+  pack_stage_kernel<<<blocks, threads, 0, s>>>(w, (uint16_t*)(plan->ws + st.b_off), g, rows, st.ci,
+                                               st.info.operand_fp16, scale);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// z [B][nz] fp32 -> bf16 hi|lo [B][2*kp] (operand of the first generator layer, train.py:312)
+// per-layer power-of-two weight scale for the fp16 forward operands: 2^k with max|w| * 2^k in [1, 2), so that both
+// halves of every weight are normal fp16 numbers; the accumulators are multiplied by 2^-k in the epilogue (exact)
 // ---------------------------------------------------------------------------------------------------
-__global__ void split_z_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zhl, int B, int nz, int kp) {
+__global__ void wmax_kernel(const float* __restrict__ w, long long n, unsigned int* __restrict__ maxbits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxbits, __float_as_uint(m));  // non-negative floats order like uints
+}
+
+__global__ void wscale_finalize_kernel(unsigned int* __restrict__ blk, int n_layers) {
+  const int l = threadIdx.x;
+  if (l >= n_layers) return;
+  const float m = __uint_as_float(blk[4 * l]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);      // m = f * 2^e, f in [0.5, 1)
+  e = max(-14, min(30, 1 - e));                   // scale = 2^(1-e): max|w| * scale in [1, 2)
+  reinterpret_cast<float*>(blk)[4 * l + 1] = ldexpf(1.f, e);
+  reinterpret_cast<float*>(blk)[4 * l + 2] = ldexpf(1.f, -e);
+}
+
+int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s) {
+  unsigned int* blk = (unsigned int*)(plan->ws + plan->off_wscale);
+  LSNF_CUDA(cudaMemsetAsync(blk, 0, (size_t)plan->n_layers * 16, s));
+  for (int l = 0; l < plan->n_layers; ++l) {
+    const auto& y = plan->layers[l];
+    const long long n = (long long)y.ci * y.co * y.k * y.k;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    wmax_kernel<<<blocks, 256, 0, s>>>(weights[l], n, blk + 4 * l);
+    LSNF_CUDA(cudaGetLastError());
+  }
+  wscale_finalize_kernel<<<1, 32, 0, s>>>(blk, plan->n_layers);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// last forward layer, second half (model.py:69-70 / :90-91 / :115-116 / :149-150): the tap-GEMM left the per-tap
+// products D[b][iy][ix][tap*nc + c]; each output pixel sums the taps that land on it (fixed order), adds the bias
+// and applies tanh.   x_hat[b][c][oy][ox] = tanh(bias[c] + sum_{ky,kx} D[b][(oy+p-ky)/s][(ox+p-kx)/s][...])
+// ---------------------------------------------------------------------------------------------------
+__global__ void last_gather_tanh_kernel(const float* __restrict__ d, const float* __restrict__ bias,
+                                        float* __restrict__ xhat, int B, int nc, int img, int hin, int k, int s,
+                                        int p, int n_pad) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * nc * img * img;
+  if (i >= total) return;
+  const int ox = (int)(i % img), oy = (int)((i / img) % img), c = (int)((i / ((long long)img * img)) % nc);
+  const int b = (int)(i / ((long long)img * img * nc));
+  float acc = bias[c];
+  for (int ky = 0; ky < k; ++ky) {
+    const int ty = oy + p - ky;
+    if (ty < 0 || ty % s) continue;
+    const int iy = ty / s;
+    if (iy >= hin) continue;
+    for (int kx = 0; kx < k; ++kx) {
+      const int tx = ox + p - kx;
+      if (tx < 0 || tx % s) continue;
+      const int ix = tx / s;
+      if (ix >= hin) continue;
+      acc += __ldcg(d + (((size_t)b * hin + iy) * hin + ix) * n_pad + (ky * k + kx) * nc + c);
+    }
+  }
+  xhat[i] = tanhf(acc);
+}
+
+int launch_last_gather(const lsnf_plan* plan, cudaStream_t s) {
+  const auto& y = plan->layers[plan->n_layers - 1];
+  const long long total = (long long)plan->cfg.batch * plan->cfg.nc * plan->img * plan->img;
+  last_gather_tanh_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      (const float*)(plan->ws + plan->off_dlast), (const float*)(plan->ws + plan->off_bias[plan->n_layers - 1]),
+      (float*)(plan->ws + plan->off_xhat), plan->cfg.batch, plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p,
+      plan->dlast_pad);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z [B][nz] fp32 -> fp16 hi|lo [B][2*kp] (operand of the first generator layer, train.py:312)
+// ---------------------------------------------------------------------------------------------------
+__global__ void split_z_kernel(const float* __restrict__ z, uint16_t* __restrict__ zhl, int B, int nz, int kp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kp) return;
   const int b = i / kp, j = i % kp;
   const float v = j < nz ? z[(size_t)b * nz + j] : 0.f;
-  __nv_bfloat16 hi, lo;
-  split_bf16(v, hi, lo);
+  uint16_t hi, lo;
+  split16(v, true, hi, lo);
   zhl[(size_t)b * 2 * kp + j] = hi;
   zhl[(size_t)b * 2 * kp + kp + j] = lo;
 }
 
 int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s) {
   const int n = plan->cfg.batch * plan->kp;
-  split_z_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, (__nv_bfloat16*)(plan->ws + plan->off_zhl), plan->cfg.batch,
+  split_z_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, (uint16_t*)(plan->ws + plan->off_zhl), plan->cfg.batch,
                                                  plan->cfg.nz, plan->kp);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
@@ -138,7 +221,7 @@ int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s) 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// fused Langevin update (train.py:324-329): one warp per sample, 4 latent elements per lane per pass
+// fused Langevin update (train.py:324-329): one CTA per sample, 4 latent elements per lane
 //   z <- z - s^2/2 (grad_g + grad_f) + s * noise ;  per-sample |grad_g|, |grad_f| ; next step's bf16 hi|lo z
 // Noise: injected eps, or Philox4x32-10 keyed by (seed, global sample index, step, element quad) drawn in
 // registers (oracle/philox.py is the checker).
@@ -165,91 +248,103 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n0 = r * cs; n1 = r * sn;
 }
 
+// One CTA per sample: 8 thread groups x 32 lanes; lane q owns latent elements [4q, 4q+4) and the groups share the
+// split-K partial sums of the reconstruction gradient (fixed summation order -> deterministic).
 __global__ void __launch_bounds__(256) langevin_update_kernel(
     float* __restrict__ z, const float* __restrict__ gg, const float* __restrict__ partial, int nsplit, int nzp,
-    const float* __restrict__ gf, const float* __restrict__ eps, __nv_bfloat16* __restrict__ zhl, int B, int nz,
+    const float* __restrict__ gf, const float* __restrict__ eps, uint16_t* __restrict__ zhl, int B, int nz,
     int kp, float step, int with_noise, uint64_t seed, uint64_t sample_offset, uint32_t step_idx,
     float* __restrict__ norm_scratch, unsigned int* __restrict__ ticket, float* __restrict__ gnorms) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp < B) {
-    const int b = warp;
-    float sg = 0.f, sf = 0.f;
-    for (int q = lane; q < nz / 4; q += 32) {
-      const size_t o = (size_t)b * nz + 4 * q;
-      float4 g;
-      if (partial) {
-        g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < nsplit; ++s) {
-          const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * nzp + 4 * q);
-          g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
-        }
-      } else {
-        g = *reinterpret_cast<const float4*>(gg + o);
+  __shared__ float4 part[8][64];
+  __shared__ float red[2][256];
+  __shared__ bool is_last;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nq = nz / 4;
+  const int grp = tid >> 5, lane = tid & 31;
+  // ---- reconstruction gradient of this sample: sum of the split-K partials (or a ready gradient) ----
+  for (int q = lane; q < nq; q += 32) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (partial) {
+#pragma unroll 4
+      for (int s = grp; s < nsplit; s += 8) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * nzp + 4 * q));
+        g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
       }
-      const float4 f = *reinterpret_cast<const float4*>(gf + o);
-      float4 v = *reinterpret_cast<const float4*>(z + o);
-      const float h = 0.5f * step * step;
-      v.x = v.x - h * (g.x + f.x); v.y = v.y - h * (g.y + f.y);
-      v.z = v.z - h * (g.z + f.z); v.w = v.w - h * (g.w + f.w);
-      if (eps) {
-        const float4 e = *reinterpret_cast<const float4*>(eps + o);
-        v.x += step * e.x; v.y += step * e.y; v.z += step * e.z; v.w += step * e.w;
-      } else if (with_noise) {
-        const uint64_t sample = sample_offset + (uint64_t)b;
-        uint32_t r[4];
-        philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), step_idx, (uint32_t)q, (uint32_t)seed,
-                      (uint32_t)(seed >> 32), r);
-        float n0, n1, n2, n3;
-        box_muller(r[0], r[1], n0, n1);
-        box_muller(r[2], r[3], n2, n3);
-        v.x += step * n0; v.y += step * n1; v.z += step * n2; v.w += step * n3;
-      }
-      *reinterpret_cast<float4*>(z + o) = v;
-      sg += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-      sf += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
-      if (zhl) {
-        __nv_bfloat16 hi[4], lo[4];
-        split_bf16(v.x, hi[0], lo[0]); split_bf16(v.y, hi[1], lo[1]);
-        split_bf16(v.z, hi[2], lo[2]); split_bf16(v.w, hi[3], lo[3]);
-        __nv_bfloat16* row = zhl + (size_t)b * 2 * kp;
-        *reinterpret_cast<uint2*>(row + 4 * q) = *reinterpret_cast<uint2*>(hi);
-        *reinterpret_cast<uint2*>(row + kp + 4 * q) = *reinterpret_cast<uint2*>(lo);
-      }
+    } else if (grp == 0) {
+      g = *reinterpret_cast<const float4*>(gg + (size_t)b * nz + 4 * q);
     }
-    if (gnorms) {
+    part[grp][q] = g;
+  }
+  __syncthreads();
+  float sg = 0.f, sf = 0.f;
+  if (tid < nq) {
+    const int q = tid;
+    float4 g = part[0][q];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sg += __shfl_xor_sync(0xffffffffu, sg, o);
-        sf += __shfl_xor_sync(0xffffffffu, sf, o);
-      }
-      if (lane == 0) { norm_scratch[b] = sqrtf(sg); norm_scratch[B + b] = sqrtf(sf); }
+    for (int k = 1; k < 8; ++k) {
+      const float4 p = part[k][q];
+      g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
+    }
+    const size_t o = (size_t)b * nz + 4 * q;
+    const float4 f = *reinterpret_cast<const float4*>(gf + o);
+    float4 v = *reinterpret_cast<const float4*>(z + o);
+    const float h = 0.5f * step * step;
+    v.x = v.x - h * (g.x + f.x); v.y = v.y - h * (g.y + f.y);
+    v.z = v.z - h * (g.z + f.z); v.w = v.w - h * (g.w + f.w);
+    if (eps) {
+      const float4 e = *reinterpret_cast<const float4*>(eps + o);
+      v.x += step * e.x; v.y += step * e.y; v.z += step * e.z; v.w += step * e.w;
+    } else if (with_noise) {
+      const uint64_t sample = sample_offset + (uint64_t)b;
+      uint32_t r[4];
+      philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), step_idx, (uint32_t)q, (uint32_t)seed,
+                    (uint32_t)(seed >> 32), r);
+      float n0, n1, n2, n3;
+      box_muller(r[0], r[1], n0, n1);
+      box_muller(r[2], r[3], n2, n3);
+      v.x += step * n0; v.y += step * n1; v.z += step * n2; v.w += step * n3;
+    }
+    *reinterpret_cast<float4*>(z + o) = v;
+    sg = g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    sf = f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+    if (zhl) {
+      __align__(8) uint16_t hi[4], lo[4];   // fp16 hi|lo operand of the first forward layer
+      split16(v.x, true, hi[0], lo[0]); split16(v.y, true, hi[1], lo[1]);
+      split16(v.z, true, hi[2], lo[2]); split16(v.w, true, hi[3], lo[3]);
+      uint16_t* row = zhl + (size_t)b * 2 * kp;
+      *reinterpret_cast<uint2*>(row + 4 * q) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(row + kp + 4 * q) = *reinterpret_cast<uint2*>(lo);
     }
   }
   if (!gnorms) return;
-  // the last block to finish averages the per-sample norms in a fixed order (deterministic diagnostics)
-  __shared__ bool is_last;
-  __shared__ float red[2][256];
-  __threadfence();
+  // per-sample norms (train.py:328-329), then the last CTA to finish averages them in a fixed order
+  red[0][tid] = sg; red[1][tid] = sf;
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { red[0][tid] += red[0][tid + o]; red[1][tid] += red[1][tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    norm_scratch[b] = sqrtf(red[0][0]);
+    norm_scratch[B + b] = sqrtf(red[1][0]);
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
   float a = 0.f, c = 0.f;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    a += __ldcg(norm_scratch + b);
-    c += __ldcg(norm_scratch + B + b);
+  for (int i = tid; i < B; i += blockDim.x) {
+    a += __ldcg(norm_scratch + i);
+    c += __ldcg(norm_scratch + B + i);
   }
-  red[0][threadIdx.x] = a; red[1][threadIdx.x] = c;
+  red[0][tid] = a; red[1][tid] = c;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + o];
-      red[1][threadIdx.x] += red[1][threadIdx.x + o];
-    }
+    if (tid < o) { red[0][tid] += red[0][tid + o]; red[1][tid] += red[1][tid + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     gnorms[0] = red[0][0] / (float)B;
     gnorms[1] = red[1][0] / (float)B;
     *ticket = 0u;
@@ -261,14 +356,12 @@ int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float*
                   uint64_t sample_offset, uint32_t step_idx, const uint32_t*, float* gnorms, int write_zhl,
                   cudaStream_t s) {
   const int B = plan->cfg.batch;
-  const int blocks = (B * 32 + 255) / 256;
-  // scalars block: [0] = ticket of the last-block-done reduction
-  unsigned int* ticket = (unsigned int*)(plan->ws + plan->off_scalars);
+  unsigned int* ticket = (unsigned int*)(plan->ws + plan->off_scalars);  // last-block-done counter
   float* scratch = (float*)(plan->ws + plan->off_norms);
-  __nv_bfloat16* zhl = (write_zhl && plan->n_layers) ? (__nv_bfloat16*)(plan->ws + plan->off_zhl) : nullptr;
-  langevin_update_kernel<<<blocks, 256, 0, s>>>(z, gg, partial, nsplit, plan->nzp, gf, eps, zhl, B, plan->cfg.nz,
-                                                plan->kp, step, with_noise, seed, sample_offset, step_idx, scratch,
-                                                ticket, gnorms);
+  uint16_t* zhl = (write_zhl && plan->n_layers) ? (uint16_t*)(plan->ws + plan->off_zhl) : nullptr;
+  langevin_update_kernel<<<B, 256, 0, s>>>(z, gg, partial, nsplit, plan->nzp, gf, eps, zhl, B, plan->cfg.nz,
+                                           plan->kp, step, with_noise, seed, sample_offset, step_idx, scratch,
+                                           ticket, gnorms);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,7 +20,8 @@ enum Epilogue : int32_t {
   EPI_ACT_HL = 0,    // + bias, LeakyReLU, split to bf16 hi|lo                 (hidden forward layers)
   EPI_OUT_TANH = 1,  // + bias, tanh, fp32 NCHW                                 (last forward layer)
   EPI_GRAD_HL = 2,   // * LeakyReLU'(saved activation), split to bf16 hi|lo     (hidden data-gradient layers)
-  EPI_PARTIAL = 3    // raw fp32 split-K partial [split][B][n_pad]              (first layer's data gradient)
+  EPI_PARTIAL = 3    // raw fp32 [split][row][n_pad]: split-K partials of the first layer's data gradient,
+                     // and the per-tap products of the last forward layer (gathered by last_gather_tanh)
 };
 
 struct TapDev {
@@ -52,6 +54,9 @@ struct StageDev {
   const __nv_bfloat16* mask;          // saved activation [B][Hg][Wg][2*oC] (EPI_GRAD_HL)
   int64_t sP, sB, sH, sW, sPos;       // output strides in elements
   int32_t nc, Ho, Wo, pad_;
+  int32_t fp16, out_fp16;             // operand / hi|lo-output element format: 1 = fp16, 0 = bf16
+  const float* descale;               // accumulators are multiplied by *descale (weights packed times 2^k), or null
+  int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
   PhaseDev ph[LSNF_MAX_PHASES];
 };
 
@@ -90,16 +95,41 @@ struct lsnf_plan {
   size_t ws_bytes = 0;
   size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
   size_t off_bias[8] = {0};
-  size_t off_norms = 0;
+  size_t off_norms = 0, off_wscale = 0, off_dlast = 0;
+  int dlast_pad = 0;
   size_t off_gradg = 0, off_gradf = 0, off_z = 0, off_flow = 0, off_scalars = 0, off_flow_out = 0;
   int ksplit_first = 1;
   char* ws = nullptr;
   bool bound = false, g_packed = false, f_packed = false, have_winv = false;
   int device = -1;
   int num_sms = 148;
+  // side stream + fork/join events: the flow prior of a Langevin iteration depends only on z, so it runs
+  // concurrently with the generator stages
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace lsnf {
+
+// ---- 16-bit hi|lo splitting: value = hi + lo, both halves in the same 16-bit float format ----
+// fp16 (11-bit significands, 22 bits together) is used where the value range is known -- activations, latents
+// and power-of-two-scaled weights of the forward pass -- so that LeakyReLU pre-activations are as exact as an fp32
+// computation; bf16 (8+8 bits, fp32 range) is used for the gradients of the backward pass.
+__device__ __forceinline__ void split16(float v, bool fp16, uint16_t& hi, uint16_t& lo) {
+  if (fp16) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+  }
+}
+__device__ __forceinline__ float join16(uint16_t hi, uint16_t lo, bool fp16) {
+  if (fp16) return __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
+  return __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo));
+}
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
@@ -115,6 +145,8 @@ int launch_tapgemm_tc(const StageHost& st, cudaStream_t s);
 int tc_encode_maps(lsnf_plan* plan, StageHost& st);
 int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w, cudaStream_t s);
 int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
+int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);
+int launch_last_gather(const lsnf_plan* plan, cudaStream_t s);
 int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
 int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s);
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
@@ -137,7 +169,7 @@ __host__ __device__ inline bool pack_index(const PackGeom& g, int ci, int co, in
                                            long long* col) {
   const int tap = ky * g.k + kx;
   if (g.kind == 0) {
-    if (g.first) {  // rows = (tap, co), cols = ci
+    if (g.first || g.last) {  // rows = (tap, co), cols = ci
       *row = (long long)tap * g.co + co;
       *col = ci;
     } else {        // rows = tap * n_pad + co, cols = ci

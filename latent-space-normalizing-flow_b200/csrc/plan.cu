@@ -109,6 +109,8 @@ static void fill_dev(lsnf_plan* p, StageHost& st) {
   }
   d.epi = I.epilogue; d.oC = I.out_channels; d.ms = I.out_mul; d.split = I.out_phase_split;
   d.leak = p->cfg.leak;
+  d.fp16 = I.operand_fp16; d.out_fp16 = (I.epilogue == EPI_ACT_HL) ? 1 : 0;
+  d.rows_total = (int64_t)p->cfg.batch * I.grid_h * I.grid_w;
   for (int ph = 0; ph < I.n_phases; ++ph) {
     d.ph[ph].ntaps = I.tap_gen_k ? I.tap_gen_k * I.tap_gen_k : I.n_taps[ph];
     d.ph[ph].mo = I.out_off_y[ph]; d.ph[ph].no = I.out_off_x[ph];
@@ -202,6 +204,12 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
     }
     for (int l = 0; l < L; ++l) p->off_bias[l] = take((size_t)p->layers[l].co * 4);
     p->off_xhat = take((size_t)B * c.nc * p->img * p->img * 4);
+    p->off_wscale = take((size_t)L * 16);   // per layer: |w|max bits, scale 2^k, descale 2^-k
+    {
+      const auto& ylast = p->layers[L - 1];
+      const int kk = ylast.k * ylast.k * ylast.co;
+      p->off_dlast = take((size_t)B * ylast.hin * ylast.hin * (kk <= 32 ? 32 : 64) * 4);
+    }
     const auto& yl = p->layers[L - 1];
     p->off_im2col = take((size_t)B * yl.hin * yl.hin * 2 * BLOCK_K * 2);
 
@@ -229,10 +237,21 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
       } else {
         I.grid_h = I.grid_w = y.hin;
         I.k_per_tap = y.ci;
-        if (st.last) { I.n_valid = y.co; I.n_pad = 16; I.block_n = 16; I.epilogue = EPI_OUT_TANH; }
-        else { I.n_valid = I.n_pad = y.co; I.block_n = pick_block_n(y.co); I.epilogue = EPI_ACT_HL; }
         I.out_channels = y.co;
-        if (y.k == 4 && y.s == 2 && y.p == 1) {
+        if (st.last) {
+          // direct product D[pos][(tap, c)] = act[pos][:] . W[:, c, tap]; last_gather_tanh sums the taps that land
+          // on each output pixel (col2im without atomics), adds the bias and applies tanh
+          if (!((y.k == 4 && y.s == 2 && y.p == 1) || (y.k == 3 && y.s == 1 && y.p == 1))) {
+            delete p; return fail(LSNF_ERR_INVALID, "unsupported last-layer geometry");
+          }
+          I.n_valid = y.k * y.k * y.co; I.n_pad = I.n_valid <= 32 ? 32 : 64; I.block_n = I.n_pad;
+          I.epilogue = EPI_PARTIAL; I.out_channels = I.n_pad;
+          I.n_phases = 1; I.out_mul = 1; I.n_taps[0] = 1; I.taps[0][0] = {0, 0, 0, 0};
+          p->dlast_pad = I.n_pad;
+        } else { I.n_valid = I.n_pad = y.co; I.block_n = pick_block_n(y.co); I.epilogue = EPI_ACT_HL; }
+        if (st.last) {
+          // taps already set (single centre tap)
+        } else if (y.k == 4 && y.s == 2 && y.p == 1) {
           I.n_phases = 4; I.out_mul = 2;
           for (int ph = 0; ph < 4; ++ph) {
             I.n_taps[ph] = up2_fwd_taps(ph >> 1, ph & 1, I.n_pad, I.taps[ph]);
@@ -246,23 +265,26 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         st.a_off = p->off_act[l - 1];
       }
       make_box(I.grid_h, I.grid_w, &I.box_b, &I.box_h, &I.box_w);
-      const int total_taps = st.first ? 1 : y.k * y.k;
-      const size_t b_rows = st.first ? (size_t)I.n_pad : (size_t)total_taps * I.n_pad;
+      const int total_taps = (st.first || st.last) ? 1 : y.k * y.k;
+      const size_t b_rows = (st.first || st.last) ? (size_t)I.n_pad : (size_t)total_taps * I.n_pad;
+      I.operand_fp16 = 1;
       I.a_h = I.grid_h; I.a_w = I.grid_w; I.tap_gen_k = 0; I.b_k = I.k_per_tap; I.b_rows = (int)b_rows;
       st.b_bytes = b_rows * 2 * I.k_per_tap * 2;
       st.b_off = take(st.b_bytes);
-      st.out_off = st.last ? p->off_xhat : p->off_act[l];
+      st.out_off = st.last ? p->off_dlast : p->off_act[l];
       st.bias_off = p->off_bias[l];
       I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
       int taps_sum = 0;
       for (int ph = 0; ph < I.n_phases; ++ph) taps_sum += I.n_taps[ph];
       I.flops = 2LL * B * I.grid_h * I.grid_w * (long long)I.n_valid * I.k_per_tap * taps_sum;
       if (st.first) I.flops = 2LL * B * (long long)I.n_valid * c.nz;
+      if (st.last) I.flops = 2LL * B * I.grid_h * I.grid_w * (long long)y.k * y.k * y.co * y.ci;
       fill_dev(p, st);
       StageDev& d = st.dev;
       d.bias_mod = y.co;
       if (st.last) {
         d.nc = c.nc; d.Ho = y.hout; d.Wo = y.hout;
+        d.bias = nullptr;
       } else {
         d.sW = 2 * y.co; d.sH = (int64_t)y.hout * d.sW; d.sB = (int64_t)y.hout * d.sH; d.sPos = d.sW; d.sP = 0;
       }
@@ -295,7 +317,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         b_rows = I.n_pad;
         const int kblocks = y.k * y.k * y.co / BLOCK_K;
         const int mtiles = (B + BLOCK_M - 1) / BLOCK_M;
-        int want = std::max(1, (2 * 148 + mtiles - 1) / mtiles);
+        int want = std::max(1, (148 + mtiles - 1) / mtiles);   // about one wave of CTAs
         int per = std::max(2, (kblocks + want - 1) / want);
         I.k_splits = (kblocks + per - 1) / per;
         per = (kblocks + I.k_splits - 1) / I.k_splits;       // what the kernels use (it_per_split)
@@ -351,7 +373,13 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
   return LSNF_OK;
 }
 
-extern "C" void lsnf_plan_destroy(lsnf_plan* plan) { delete plan; }
+extern "C" void lsnf_plan_destroy(lsnf_plan* plan) {
+  if (!plan) return;
+  if (plan->side) cudaStreamDestroy(plan->side);
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  delete plan;
+}
 
 extern "C" size_t lsnf_workspace_bytes(const lsnf_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -400,12 +428,18 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
     d.a = (const __nv_bfloat16*)(plan->ws + st.a_off);
     d.b = (const __nv_bfloat16*)(plan->ws + st.b_off);
     d.out = plan->ws + st.out_off;
-    d.bias = st.kind == 0 ? (const float*)(plan->ws + st.bias_off) : nullptr;
+    d.bias = (st.kind == 0 && !st.last) ? (const float*)(plan->ws + st.bias_off) : nullptr;
+    d.descale = st.kind == 0 ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 8) : nullptr;
     d.mask = (st.kind == 1 && !st.first) ? (const __nv_bfloat16*)(plan->ws + st.mask_off) : nullptr;
     if (plan->cfg.gemm_impl == LSNF_GEMM_TCGEN05) {
       int rc = tc_encode_maps(plan, st);
       if (rc) return rc;
     }
+  }
+  if (!plan->side) {
+    LSNF_CUDA(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
+    LSNF_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+    LSNF_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
   }
   plan->bound = true;
   plan->g_packed = plan->f_packed = false;
@@ -430,6 +464,10 @@ extern "C" int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* 
   if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
   if (n_layers != plan->n_layers || !weights || !biases) return fail(LSNF_ERR_INVALID, "layer count mismatch");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = launch_weight_scales(plan, weights, s);
+    if (rc) return rc;
+  }
   for (auto& st : plan->stages) {
     int rc = launch_pack_stage(plan, st, weights[st.layer], s);
     if (rc) return rc;
@@ -459,6 +497,7 @@ static int gen_forward(lsnf_plan* p, const float* z, float* x_hat, cudaStream_t 
   if (split && (rc = launch_split_z(p, z, s))) return rc;
   for (int l = 0; l < p->n_layers; ++l)
     if ((rc = run_stage(p, p->stages[l], s))) return rc;
+  if ((rc = launch_last_gather(p, s))) return rc;
   if (x_hat) {
     const size_t bytes = (size_t)p->cfg.batch * p->cfg.nc * p->img * p->img * 4;
     LSNF_CUDA(cudaMemcpyAsync(x_hat, p->ws + p->off_xhat, bytes, cudaMemcpyDeviceToDevice, s));
@@ -472,6 +511,13 @@ static int gen_dgrad_partial(lsnf_plan* p, const float* x, float sigma, cudaStre
   for (int i = p->n_layers; i < 2 * p->n_layers; ++i)
     if ((rc = run_stage(p, p->stages[i], s))) return rc;
   return LSNF_OK;
+}
+
+extern "C" int lsnf_plan_run_stage(lsnf_plan* plan, int32_t index, lsnf_stream stream) {
+  int rc = need(plan, true, false);
+  if (rc) return rc;
+  if (index < 0 || index >= (int)plan->stages.size()) return fail(LSNF_ERR_INVALID, "bad stage index");
+  return run_stage(plan, plan->stages[index], (cudaStream_t)stream);
 }
 
 extern "C" int lsnf_generator_forward(lsnf_plan* plan, const float* z, float* x_hat, lsnf_stream stream) {
@@ -517,8 +563,8 @@ extern "C" int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad
 
 extern "C" int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps) {
   if (!plan) return 0;
-  // per step: L forward + im2col + L data-gradient + flow + update; once: split_z
-  return 1 + steps * (2 * plan->n_layers + 3);
+  // per step: L forward + gather/tanh + im2col + L data-gradient + flow + update; once: split_z
+  return 1 + steps * (2 * plan->n_layers + 4);
 }
 
 extern "C" int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t steps, float step_size,
@@ -536,9 +582,14 @@ extern "C" int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* 
   LSNF_CUDA(cudaMemcpyAsync(z, z0, zbytes, cudaMemcpyDeviceToDevice, s));
   if ((rc = launch_split_z(plan, z, s))) return rc;
   for (int t = 0; t < steps; ++t) {
+    // fork: the flow prior (train.py:316-323) only needs z; it overlaps the generator stages on the side stream
+    LSNF_CUDA(cudaEventRecord(plan->ev_fork, s));
+    LSNF_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+    if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, plan->side))) return rc;
+    LSNF_CUDA(cudaEventRecord(plan->ev_join, plan->side));
     if ((rc = gen_forward(plan, z, nullptr, s, false))) return rc;
     if ((rc = gen_dgrad_partial(plan, x, sigma, s))) return rc;
-    if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, s))) return rc;
+    LSNF_CUDA(cudaStreamWaitEvent(s, plan->ev_join, 0));
     const float* e = eps ? eps + (size_t)t * c.batch * c.nz : nullptr;
     if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gf, step_size, e, with_noise, seed,
                             sample_offset, (uint32_t)t, nullptr, t == steps - 1 ? gnorms : nullptr, 1, s)))

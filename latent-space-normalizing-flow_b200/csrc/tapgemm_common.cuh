@@ -25,21 +25,25 @@ __device__ __forceinline__ RowCtx tile_row(const StageDev& st, int mtile, int r)
   return rc;
 }
 
-__device__ __forceinline__ void split_pack(const float* v, int n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  for (int j = 0; j < n; ++j) {
-    hi[j] = __float2bfloat16_rn(v[j]);
-    lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
-  }
+template <int NV>
+__device__ __forceinline__ void split_pack(const float* v, bool fp16, uint16_t* hi, uint16_t* lo) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) split16(v[j], fp16, hi[j], lo[j]);
 }
 
 // Applies the stage's epilogue to NV consecutive accumulator columns [col, col+NV) of one row and stores them.
-// NV is 4 or 8; col % NV == 0.  Reference semantics: bias + LeakyReLU / Tanh of model.py:56-151, and for the
-// data gradient the LeakyReLU derivative autograd applies (train.py:314).
+// NV is 4 or 8; col % NV == 0.  Reference semantics: bias + LeakyReLU of model.py:56-151, and for the data gradient
+// the LeakyReLU derivative autograd applies (train.py:314).  `pre_mask` (optional) holds the NV saved-activation
+// halves already fetched by the caller.
 template <int NV>
 __device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, int split_idx, const RowCtx& rc,
-                                               int col, const float* acc) {
+                                               int col, const float* acc_in, float descale,
+                                               const uint16_t* pre_mask = nullptr) {
   if (!rc.valid || col >= st.n_pad) return;
   using Vec = typename std::conditional<NV == 8, uint4, uint2>::type;
+  float acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = acc_in[j] * descale;
   if (st.epi == EPI_ACT_HL) {
     const int pos = col / st.oC, cb = col % st.oC;
     const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
@@ -49,46 +53,40 @@ __device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, in
       const float t = acc[j] + __ldg(st.bias + (col + j) % st.bias_mod);
       v[j] = t > 0.f ? t : t * st.leak;
     }
-    __align__(16) __nv_bfloat16 hi[NV], lo[NV];
-    split_pack(v, NV, hi, lo);
-    __nv_bfloat16* o = (__nv_bfloat16*)st.out + (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW +
-                       (size_t)pos * st.sPos + cb;
+    __align__(16) uint16_t hi[NV], lo[NV];
+    split_pack<NV>(v, st.out_fp16 != 0, hi, lo);
+    uint16_t* o = (uint16_t*)st.out + (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW +
+                  (size_t)pos * st.sPos + cb;
     *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
     *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
-  } else if (st.epi == EPI_OUT_TANH) {
-    const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
-    float* o = (float*)st.out;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c = col + j;
-      if (c < st.nc) o[(((size_t)rc.b * st.nc + c) * st.Ho + mo) * st.Wo + no] = tanhf(acc[j] + __ldg(st.bias + c));
-    }
   } else if (st.epi == EPI_GRAD_HL) {
-    const __nv_bfloat16* mk = st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + col;
-    __align__(16) __nv_bfloat16 mv[NV];
-    *reinterpret_cast<Vec*>(mv) = *reinterpret_cast<const Vec*>(mk);
+    __align__(16) uint16_t mv[NV];
+    if (pre_mask) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) mv[j] = pre_mask[j];
+    } else {
+      const uint16_t* mk = (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + col;
+      *reinterpret_cast<Vec*>(mv) = *reinterpret_cast<const Vec*>(mk);
+    }
     float v[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = __bfloat162float(mv[j]) > 0.f ? acc[j] : acc[j] * st.leak;
-    __align__(16) __nv_bfloat16 hi[NV], lo[NV];
-    split_pack(v, NV, hi, lo);
+    for (int j = 0; j < NV; ++j) v[j] = (mv[j] & 0x8000u) ? acc[j] * st.leak : acc[j];  // sign bit of the saved activation
+    __align__(16) uint16_t hi[NV], lo[NV];
+    split_pack<NV>(v, st.out_fp16 != 0, hi, lo);
     size_t off;
     if (st.split)
       off = (size_t)((rc.m & 1) * 2 + (rc.n & 1)) * st.sP + (size_t)rc.b * st.sB + (size_t)(rc.m >> 1) * st.sH +
             (size_t)(rc.n >> 1) * st.sW;
     else
       off = (size_t)rc.b * st.sB + (size_t)rc.m * st.sH + (size_t)rc.n * st.sW;
-    __nv_bfloat16* o = (__nv_bfloat16*)st.out + off + col;
+    uint16_t* o = (uint16_t*)st.out + off + col;
     *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
     *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
-  } else {  // EPI_PARTIAL
-    float* o = (float*)st.out + ((size_t)split_idx * st.B + rc.b) * st.n_pad + col;
-    if (NV == 8) {
-      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
-      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    }
+  } else {  // EPI_PARTIAL: raw fp32 rows
+    const size_t row = ((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n;
+    float* o = (float*)st.out + ((size_t)split_idx * st.rows_total + row) * st.n_pad + col;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (NV == 8) *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 

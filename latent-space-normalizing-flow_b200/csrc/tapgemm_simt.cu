@@ -40,16 +40,17 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
     get_tap(st, phase, t, dy, dx, plane, brow, bcol);
     const int y = a_m + dy, x = a_n + dx;
     const bool a_ok = a_b < st.B && y >= 0 && y < st.aH && x >= 0 && x < st.aW;
-    const __nv_bfloat16* arow =
-        st.a + ((((size_t)plane * st.B + a_b) * st.aH + y) * st.aW + x) * 2 * st.Ka + kb * BLOCK_K;
+    const uint16_t* arow = (const uint16_t*)st.a +
+                           ((((size_t)plane * st.B + a_b) * st.aH + y) * st.aW + x) * 2 * st.Ka + kb * BLOCK_K;
     const int brow_i = brow + n0 + bn;
     const bool b_ok = brow_i < st.b_rows && (n0 + bn) < st.n_pad;
-    const __nv_bfloat16* brw = st.b + (size_t)brow_i * 2 * st.b_k + bcol + kb * BLOCK_K;
+    const uint16_t* brw = (const uint16_t*)st.b + (size_t)brow_i * 2 * st.b_k + bcol + kb * BLOCK_K;
+    const bool f16 = st.fp16 != 0;
     for (int slab = 0; slab < BLOCK_K / SIMT_KS; ++slab) {
       {
-        __align__(16) __nv_bfloat16 hi[16], lo[16];
+        __align__(16) uint16_t hi[16], lo[16];
         if (a_ok) {
-          const __nv_bfloat16* p = arow + slab * SIMT_KS + ah * 16;
+          const uint16_t* p = arow + slab * SIMT_KS + ah * 16;
           *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(p);
           *reinterpret_cast<uint4*>(hi + 8) = *reinterpret_cast<const uint4*>(p + 8);
           *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(p + st.Ka);
@@ -57,18 +58,18 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          As[ah * 16 + i][ar] = a_ok ? __bfloat162float(hi[i]) + __bfloat162float(lo[i]) : 0.f;
+          As[ah * 16 + i][ar] = a_ok ? join16(hi[i], lo[i], f16) : 0.f;
       }
       {
-        __align__(16) __nv_bfloat16 hi[8], lo[8];
+        __align__(16) uint16_t hi[8], lo[8];
         if (b_ok) {
-          const __nv_bfloat16* p = brw + slab * SIMT_KS + bq * 8;
+          const uint16_t* p = brw + slab * SIMT_KS + bq * 8;
           *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(p);
           *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(p + st.b_k);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          Bs[bq * 8 + i][bn] = b_ok ? __bfloat162float(hi[i]) + __bfloat162float(lo[i]) : 0.f;
+          Bs[bq * 8 + i][bn] = b_ok ? join16(hi[i], lo[i], f16) : 0.f;
       }
       __syncthreads();
 #pragma unroll 8
@@ -86,10 +87,11 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
       __syncthreads();
     }
   }
+  const float descale = st.descale ? __ldg(st.descale) : 1.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const RowCtx rc = tile_row(st, mtile, ty * 8 + i);
-    epilogue_store<4>(st, phase, split, rc, n0 + tx * 4, acc[i]);
+    epilogue_store<4>(st, phase, split, rc, n0 + tx * 4, acc[i], descale);
   }
 }
 

@@ -5,9 +5,10 @@
 //
 // * A rows are 128 grid positions (b, m, n) fetched by ONE 5-D TMA box per tap and K block; the (dy, dx) shift
 //   moves the box, and TMA's out-of-bounds zero fill supplies the convolution padding and the ragged batch.
-// * Operands are bf16 hi|lo pairs (value = hi + lo); each K step issues three tcgen05.mma (hi*hi, hi*lo, lo*hi)
-//   into one fp32 TMEM accumulator -- the 3-pass split that keeps z_T within the 1e-4 parity budget.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// * Operands are 16-bit hi|lo pairs (value = hi + lo; fp16 for the forward pass, bf16 for the data gradients); each
+//   K step issues three tcgen05.mma (lo*hi, hi*lo, hi*hi) into one fp32 TMEM accumulator -- the 3-pass split that
+//   keeps z_T within the 1e-4 parity budget.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
 //   (tcgen05.ld -> bias/activation/derivative -> bf16 hi|lo or fp32 stores).
 #include <type_traits>
 
@@ -15,7 +16,8 @@
 
 namespace lsnf {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half the columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB per hi or lo half
 
 template <int BN>
@@ -23,6 +25,7 @@ struct TcCfg {
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+  static constexpr int SPAN = BN >= 64 ? BN / 2 : BN;   // columns per epilogue warp
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
@@ -73,9 +76,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 
 template <int BN>
-__device__ __forceinline__ constexpr uint32_t umma_idesc() {
-  // c_format F32 (bits 4-5 = 1), a/b format BF16 (bits 7-9, 10-12 = 1), K-major A and B, N>>3 at 17, M>>4 at 24
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(bool fp16) {
+  // c_format F32 (bits 4-5 = 1), a/b format (bits 7-9, 10-12): 0 = F16, 1 = BF16; K-major A and B;
+  // N>>3 at bit 17, M>>4 at bit 24
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -180,7 +185,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc<BN>();
+      const uint32_t idesc = umma_idesc<BN>(st.fp16 != 0);
       for (int it = it0; it < it1; ++it) {
         const int i = it - it0, s = i % Cfg::STAGES;
         const uint32_t par = (uint32_t)((i / Cfg::STAGES) & 1);
@@ -201,24 +206,43 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       umma_commit(tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps w and w+4 split the columns =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const RowCtx rc = tile_row(st, mtile, r);
+    constexpr int SPAN = Cfg::SPAN;
+    constexpr int CH = SPAN >= 32 ? 32 : 16;
+    const int c_begin = half * SPAN;
+    const bool active = c_begin < BN;
+    // the saved-activation signs this row needs are fetched while the main loop is still running
+    uint4 mk[SPAN / 8];
+    const bool use_mask = st.epi == EPI_GRAD_HL && active && rc.valid;
+    if (use_mask) {
+      const uint4* mp = reinterpret_cast<const uint4*>(
+          (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + n0 + c_begin);
+#pragma unroll
+      for (int j = 0; j < SPAN / 8; ++j) mk[j] = __ldg(mp + j);
+    }
+    const float descale = st.descale ? __ldg(st.descale) : 1.f;
     if (it1 > it0) mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    constexpr int CH = BN >= 32 ? 32 : 16;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += CH) {
-      uint32_t v[CH];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
-      if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float f[CH];
+    if (active) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = (it1 > it0) ? __uint_as_float(v[j]) : 0.f;
+      for (int cc = 0; cc < SPAN; cc += CH) {
+        const int c = c_begin + cc;
+        uint32_t v[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
+        if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float f[CH];
 #pragma unroll
-      for (int j = 0; j < CH; j += 8) epilogue_store<8>(st, phase, split, rc, n0 + c + j, f + j);
+        for (int j = 0; j < CH; ++j) f[j] = (it1 > it0) ? __uint_as_float(v[j]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < CH; j += 8)
+          epilogue_store<8>(st, phase, split, rc, n0 + c + j, f + j, descale,
+                            use_mask ? reinterpret_cast<const uint16_t*>(&mk[(cc + j) / 8]) : nullptr);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,6 +331,7 @@ int launch_tapgemm_tc(const StageHost& sh, cudaStream_t s) {
     case 256: return launch_bn<256>(sh, s);
     case 128: return launch_bn<128>(sh, s);
     case 64: return launch_bn<64>(sh, s);
+    case 32: return launch_bn<32>(sh, s);
     case 16: return launch_bn<16>(sh, s);
     default: set_error("unsupported N tile"); return LSNF_ERR_INVALID;
   }

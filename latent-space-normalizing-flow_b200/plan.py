@@ -79,6 +79,10 @@ class Plan:
             out.append(info)
         return out
 
+    def run_stage(self, index: int) -> None:
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.lsnf_plan_run_stage(self.handle, int(index), _stream(self.device)), "lsnf_plan_run_stage")
+
     def launch_count(self, steps: int) -> int:
         return int(self.lib.lsnf_langevin_launch_count(self.handle, steps))
 

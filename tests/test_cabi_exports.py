@@ -16,7 +16,7 @@ def declared_functions():
 def test_every_declared_symbol_is_exported_and_bound():
     lib = _cabi.load()
     names = declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), f"{n} declared in lsnf.h but not exported"
         assert n in _cabi.EXPORTS, f"{n} has no ctypes prototype in _cabi.py"
@@ -29,5 +29,5 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.Config) == 4 * 16
     assert C.sizeof(_cabi.Tap) == 16
     # kind..n_phases (12) + n_taps (4) + taps (4*16*4) + out_mul (1) + off_y/x (8) + 11 ints, then 4 int64
-    ints = 12 + 4 + 4 * 16 * 4 + 1 + 8 + 10
+    ints = 12 + 4 + 4 * 16 * 4 + 1 + 8 + 11
     assert C.sizeof(_cabi.StageInfo) == (ints * 4 + 7) // 8 * 8 + 32

@@ -1,0 +1,158 @@
+"""GPU parity of the generator tap-GEMMs and of the whole Langevin loop, through the C ABI, against the fixtures
+written from the reference's own modules (tests/golden) and against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import lsnf_b200
+from lsnf_b200 import _cabi, synth
+from oracle import refpath
+from helpers import REL_TOL, assert_grad_close, load_golden, rel_err, rel_l2, to_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+IMPLS = {"tcgen05": _cabi.GEMM_TCGEN05, "simt": _cabi.GEMM_SIMT}
+
+
+def build(c, impl="tcgen05", seed=1):
+    args = lsnf_b200.make_args(dataset=c["dataset"], nz=c["nz"], ngf=c["ngf"], f_width=c.get("f_width", 64),
+                               f_flow_coupling=c.get("coupling", 1), g_llhd_sigma=c.get("sigma", 0.3),
+                               g_l_steps=c.get("T", 20))
+    netG = lsnf_b200._netG(args).to(DEV).eval()
+    netF = lsnf_b200._netF(args, nz=c["nz"]).to(DEV).eval()
+    netG.load_state_dict(to_torch(synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=seed)))
+    netF.load_state_dict(to_torch(synth.flow_state(c["nz"], c.get("f_width", 64), 5, c.get("coupling", 1), 2, seed=seed)))
+    netG.gemm_impl = IMPLS[impl]
+    return args, netG, netF
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("name", ["svhn_small", "cifar_small", "celeba_small"])
+def test_generator_forward_and_reconstruction_gradient(name, impl):
+    g = load_golden(name)
+    c = g["config"]
+    args, netG, netF = build(c, impl)
+    z0 = torch.from_numpy(g["z0"]).to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    with torch.no_grad():
+        xh = netG(z0)                                    # reference call site train.py:312
+    assert xh.shape == g["x_hat"].shape
+    assert rel_err(xh.cpu(), g["x_hat"]) < REL_TOL       # 1e-4 relative (fp32), north_star
+    plan = netG._plan(c["B"], torch.device(DEV))
+    gg = plan.generator_dgrad(x, c["sigma"])             # train.py:313-314
+    assert_grad_close(gg.cpu(), g["grad_g"].reshape(c["B"], c["nz"]), what=f"grad_g {name}/{impl}")
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("name", ["svhn_small", "cifar_small", "celeba_small", "svhn_additive"])
+def test_langevin_matches_reference_fixture(name, impl):
+    g = load_golden(name)
+    c = g["config"]
+    args, netG, netF = build(c, impl)
+    z0 = torch.from_numpy(g["z0"]).to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, eps=torch.from_numpy(g["eps"]).to(DEV))
+    assert z.shape == (c["B"], c["nz"], 1, 1) and gn.dim() == 0 and fn.dim() == 0
+    assert rel_l2(z.cpu(), g["z_T"]) < REL_TOL and rel_err(z.cpu(), g["z_T"]) < REL_TOL
+    assert abs(gn.item() - g["gnorm_g"]) < REL_TOL * g["gnorm_g"] * 10
+    assert abs(fn.item() - g["gnorm_f"]) < REL_TOL * g["gnorm_f"] * 10
+    # test-mode variant: no noise (train.py:623-625)
+    zn, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, with_noise=False)
+    assert rel_l2(zn.cpu(), g["z_T_nonoise"]) < REL_TOL
+    assert torch.equal(z0.cpu(), torch.from_numpy(g["z0"])), "inputs must not be modified"
+
+
+def test_langevin_long_chain_against_oracle_divergence_curve():
+    # 20 steps at the SVHN training configuration shape (ngf reduced for CPU-oracle time); the per-step error
+    # curve must stay inside the tolerance, not only the end point (hard parts)
+    c = dict(dataset="svhn", nz=100, ngf=32, B=16, T=20, sigma=0.3)
+    args, netG, netF = build(c, seed=4)
+    x_np, z0_np, eps_np = synth.inputs(c["B"], c["nz"], 3, 32, c["T"], seed=4)
+    trace = []
+    refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np), to_torch(synth.generator_state("svhn", 100, 32, 3, 4)),
+                     to_torch(synth.flow_state(100, 64, 5, 1, 2, 4)), refpath.generator_layers("svhn", 100, 32),
+                     depth=5, steps=c["T"], step_size=0.1, sigma=0.3, eps=torch.from_numpy(eps_np), trace=trace)
+    z0, x, eps = (torch.from_numpy(a).to(DEV) for a in (z0_np, x_np, eps_np))
+    curve = []
+    for t in (1, 5, 10, 20):
+        z, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, eps=eps[:t], steps=t)
+        curve.append(rel_l2(z.cpu(), trace[t - 1]))
+    print("divergence curve (steps 1,5,10,20):", curve)
+    assert max(curve) < REL_TOL
+
+
+@pytest.mark.parametrize("batch", [57, 100, 130])
+def test_ragged_and_multi_tile_batches(batch):
+    # ragged last batch of SVHN (73 257 mod 100 = 57), the reference batch, and more than one 128-row tile
+    c = dict(dataset="svhn", nz=100, ngf=32, B=batch, sigma=0.3)
+    args, netG, netF = build(c)
+    x_np, z0_np, _ = synth.inputs(batch, 100, 3, 32, 1, seed=batch)
+    xh_ref, gg_ref = refpath.recon_grad(torch.from_numpy(z0_np), torch.from_numpy(x_np),
+                                        to_torch(synth.generator_state("svhn", 100, 32)),
+                                        refpath.generator_layers("svhn", 100, 32), 0.3)
+    z0, x = torch.from_numpy(z0_np).to(DEV), torch.from_numpy(x_np).to(DEV)
+    xh = netG.generate(z0)
+    gg = netG._plan(batch, torch.device(DEV)).generator_dgrad(x, 0.3)
+    assert rel_err(xh.cpu(), xh_ref) < REL_TOL
+    assert_grad_close(gg.cpu(), gg_ref.reshape(batch, 100), what=f"grad_g B={batch}")
+
+
+def test_philox_langevin_is_invariant_to_batch_sharding_and_deterministic():
+    # full CIFAR-10 configuration (nz=128, ngf=128, B=100): chains are independent per sample and the noise is
+    # keyed by the global sample index, so two half-batches reproduce the full batch bit for bit
+    c = dict(dataset="cifar10", nz=128, ngf=128, B=100, sigma=0.3, T=3)
+    args, netG, netF = build(c)
+    x_np, z0_np, _ = synth.inputs(100, 128, 3, 32, 1, seed=11)
+    z0, x = torch.from_numpy(z0_np).to(DEV), torch.from_numpy(x_np).to(DEV)
+    full, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, seed=77)
+    again, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, seed=77)
+    assert torch.equal(full, again)
+    a, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0[:50], x[:50], netG, netF, args, seed=77, sample_offset=0)
+    b, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0[50:], x[50:], netG, netF, args, seed=77, sample_offset=50)
+    assert torch.equal(torch.cat([a, b]), full)
+    other, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, seed=78)
+    assert not torch.equal(other, full)
+    assert torch.isfinite(full).all() and gn.item() > 0 and fn.item() > 0
+
+
+def test_cifar_full_config_one_step_against_oracle():
+    # one Langevin step of the headline configuration at a batch the CPU oracle finishes in seconds
+    c = dict(dataset="cifar10", nz=128, ngf=128, B=8, sigma=0.3, T=2)
+    args, netG, netF = build(c)
+    x_np, z0_np, eps_np = synth.inputs(8, 128, 3, 32, 2, seed=2)
+    zr, gnr, fnr = refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np),
+                                    to_torch(synth.generator_state("cifar10", 128, 128)),
+                                    to_torch(synth.flow_state(128, 64)), refpath.generator_layers("cifar10", 128, 128),
+                                    depth=5, steps=2, step_size=0.1, sigma=0.3, eps=torch.from_numpy(eps_np))
+    z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(
+        torch.from_numpy(z0_np).to(DEV), torch.from_numpy(x_np).to(DEV), netG, netF, args,
+        eps=torch.from_numpy(eps_np).to(DEV))
+    assert rel_l2(z.cpu(), zr) < REL_TOL
+    assert abs(gn.item() - gnr.item()) < 1e-3 * gnr.item() and abs(fn.item() - fnr.item()) < 1e-3 * fnr.item()
+
+
+def test_module_interface_and_checkpoint_keys():
+    c = dict(dataset="svhn", nz=100, ngf=32, B=4)
+    args, netG, netF = build(c)
+    keys = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "state_dict_keys.npz"))
+    assert sorted(netF.state_dict().keys()) == sorted(str(s) for s in keys["flow_nz100_w64"])
+    assert list(netG.state_dict().keys()) == [str(s).split(":")[0] for s in keys["gen_svhn"]]
+    # prior sampling call sites (train.py:433-437, :567-576)
+    xs = lsnf_b200.sample_x(netG, netF, 4, DEV, generator=torch.Generator(DEV).manual_seed(0))
+    assert xs.shape == (4, 3, 32, 32) and float(xs.min()) >= 0.0 and float(xs.max()) <= 1.0
+    with torch.no_grad():
+        zs = torch.randn(4, 100, 1, 1, device=DEV)
+        zf = netF(torch.squeeze(zs), objective=torch.zeros(4, device=DEV), reverse=True, return_obj=False)
+        xk = netG(torch.reshape(zf, (4, 100, 1, 1)))
+    assert xk.shape == (4, 3, 32, 32)
+    # the training-mode autograd branch (parameter updates, out of the hot-path scope) agrees with the kernels
+    netG.train()
+    z = torch.randn(4, 100, 1, 1, device=DEV)
+    x_eager = netG(z)
+    assert x_eager.requires_grad
+    netG.eval()
+    assert rel_err(netG(z).cpu(), x_eager.detach().cpu()) < 1e-3   # eager cuDNN may use TF32
+    with pytest.raises(RuntimeError):
+        netG.generate(z.cpu())                                       # no CPU fallback
+    with pytest.raises(ValueError):
+        lsnf_b200._netG(lsnf_b200.make_args(dataset="svhn") | {"dataset": "mnist"})

@@ -97,6 +97,22 @@ def test_stage_tables_reproduce_conv_transpose_and_its_data_gradient(arch, nz, n
         got = np.zeros((B, hout, hout, co))
         if l == 0:
             got = d[0][:, 0, 0, : fi.n_valid].reshape(B, k, k, co)
+        elif l == L - 1:
+            # direct product + gather (last_gather_tanh_kernel): every output pixel sums the taps that land on it
+            assert fi.epilogue == 3 and fi.n_phases == 1 and fi.n_valid == k * k * co and fi.n_pad in (32, 64)
+            dd = d[0]
+            for oy in range(hout):
+                for ox in range(hout):
+                    for ky in range(k):
+                        ty = oy + p - ky
+                        if ty < 0 or ty % s or ty // s >= hin:
+                            continue
+                        for kx in range(k):
+                            tx = ox + p - kx
+                            if tx < 0 or tx % s or tx // s >= hin:
+                                continue
+                            t = ky * k + kx
+                            got[:, oy, ox, :] += dd[:, ty // s, tx // s, t * co:(t + 1) * co]
         else:
             for ph in range(fi.n_phases):
                 got[:, fi.out_off_y[ph]::fi.out_mul, fi.out_off_x[ph]::fi.out_mul, :] = d[ph][..., :co]
@@ -157,5 +173,5 @@ def test_compute_entry_points_fail_loudly_without_binding():
     assert lib.lsnf_generator_forward(h, None, None, None) == -3          # LSNF_ERR_STATE: not bound
     assert b"bind" in lib.lsnf_last_error()
     assert lib.lsnf_workspace_bytes(h) > 0
-    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 3)
+    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 4)
     lib.lsnf_plan_destroy(h)
