@@ -416,14 +416,22 @@ static size_t flow_smem_floats(const FlowLayout& f, int S, int depth, bool stash
 
 template <int S>
 static int launch_fwd_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
-  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t cur = 0;   // raised lazily, outside any stream capture (the first call of a plan is eager)
+  if (smem > cur) {
+    LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
   flow_forward_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
 template <int S>
 static int launch_inv_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
-  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t cur = 0;
+  if (smem > cur) {
+    LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
   flow_inverse_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;

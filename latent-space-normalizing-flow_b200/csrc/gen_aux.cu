@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(256) langevin_update_kernel(
     float* __restrict__ z, const float* __restrict__ gg, const float* __restrict__ partial, int nsplit, int nzp,
     const float* __restrict__ gf, const float* __restrict__ eps, uint16_t* __restrict__ zhl, int B, int nz,
     int kp, float step, int with_noise, uint64_t seed, uint64_t sample_offset, uint32_t step_idx,
-    float* __restrict__ norm_scratch, unsigned int* __restrict__ ticket, float* __restrict__ gnorms) {
+    const uint64_t* __restrict__ dyn, float* __restrict__ norm_scratch, unsigned int* __restrict__ ticket,
+    float* __restrict__ gnorms) {
   __shared__ float4 part[8][64];
+  if (dyn) { seed = dyn[0]; sample_offset = dyn[1]; }   // per-call values of a replayed CUDA graph
   __shared__ float red[2][256];
   __shared__ bool is_last;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -353,15 +355,25 @@ __global__ void __launch_bounds__(256) langevin_update_kernel(
 
 int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit,
                   const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
-                  uint64_t sample_offset, uint32_t step_idx, const uint32_t*, float* gnorms, int write_zhl,
+                  uint64_t sample_offset, uint32_t step_idx, const uint64_t* dyn, float* gnorms, int write_zhl,
                   cudaStream_t s) {
   const int B = plan->cfg.batch;
   unsigned int* ticket = (unsigned int*)(plan->ws + plan->off_scalars);  // last-block-done counter
   float* scratch = (float*)(plan->ws + plan->off_norms);
   uint16_t* zhl = (write_zhl && plan->n_layers) ? (uint16_t*)(plan->ws + plan->off_zhl) : nullptr;
   langevin_update_kernel<<<B, 256, 0, s>>>(z, gg, partial, nsplit, plan->nzp, gf, eps, zhl, B, plan->cfg.nz,
-                                           plan->kp, step, with_noise, seed, sample_offset, step_idx, scratch,
+                                           plan->kp, step, with_noise, seed, sample_offset, step_idx, dyn, scratch,
                                            ticket, gnorms);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+__global__ void set_dyn_kernel(uint64_t* dyn, uint64_t seed, uint64_t sample_offset) {
+  dyn[0] = seed; dyn[1] = sample_offset;
+}
+
+int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, cudaStream_t s) {
+  set_dyn_kernel<<<1, 1, 0, s>>>((uint64_t*)(plan->ws + plan->off_dyn), seed, sample_offset);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }

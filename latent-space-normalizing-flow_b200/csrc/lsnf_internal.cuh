@@ -107,6 +107,14 @@ struct lsnf_plan {
   // concurrently with the generator stages
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // CUDA graphs of the whole g_l_steps loop, keyed by (steps, step_size, sigma, with_noise); per-call values
+  // (seed, sample offset) are read from device memory, inputs are staged into the workspace
+  struct LoopGraph { int steps; float step_size, sigma; int with_noise; cudaGraphExec_t exec; };
+  std::vector<LoopGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  size_t off_x = 0, off_gnorms = 0, off_dyn = 0;
+  long long runs = 0;
+  bool use_graphs = true;
 };
 
 namespace lsnf {
@@ -157,8 +165,9 @@ int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, flo
 int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s);
 int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit,
                   const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
-                  uint64_t sample_offset, uint32_t step_idx, const uint32_t* step_ctr, float* gnorms,
+                  uint64_t sample_offset, uint32_t step_idx, const uint64_t* dyn, float* gnorms,
                   int write_zhl, cudaStream_t s);
+int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, cudaStream_t s);
 
 // (row, col) of W[ci][co][ky][kx] in the packed B operand of a stage; shared by host and device
 struct PackGeom {
