@@ -21,12 +21,126 @@ struct FlowArgs {
 
 constexpr int FLOW_THREADS = 256;
 
-// out[s][j] = epi(s, j, sum_k in[s][k] * M[k*N + j]) for s < S, j < N.  M is row-major [K][N] in global
-// memory (read once per CTA, coalesced along j); `in` and `out` live in shared memory.  The K range is split
-// across 256/Nr thread groups whose partial sums meet in `scratch`.
+// ---- shared-memory staging of the parameters: cp.async.bulk (1-D TMA) + mbarrier, double-buffered ----
+// Every matrix of the coupling layers is streamed global -> shared while the previous mat-vec computes, and the
+// per-step vectors (actnorm b / exp(3 logs), MLP biases and scales) travel as one block per step; the mat-vecs then
+// read shared memory only ("the small coupling MLPs stay SMEM-resident").
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void f_bulk_load(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct Feeder {
+  const float* params;
+  FlowLayout f;
+  int depth, perm2, with_bwd, inverse;
+  float* mbuf[2];
+  float* vbuf[2];
+  uint32_t mbar[2], vbar[2];
+  uint32_t m, v;          // next matrix / vector-block item to be consumed
+  int n_mat, n_vec, ipl;  // items in the whole launch, matrices per step
+
+  // matrix item -> (offset, floats).  forward pass: per step [W] W1 W2 W3; backward: per step (descending) W3T W2T
+  // W1T [WT]; inverse pass: per step (descending) W1 W2 W3 [Winv]
+  __device__ __forceinline__ void mat_item(int idx, size_t& off, uint32_t& n) const {
+    const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
+    int L, j;
+    bool bwd = false;
+    if (inverse) { L = depth - 1 - idx / ipl; j = idx % ipl; }
+    else if (idx < depth * ipl) { L = idx / ipl; j = idx % ipl + (perm2 ? 0 : 1); }
+    else { bwd = true; idx -= depth * ipl; L = depth - 1 - idx / ipl; j = idx % ipl; }
+    size_t o; uint32_t c;
+    if (inverse) {
+      if (j == 0) { o = f.W1; c = half * w; } else if (j == 1) { o = f.W2; c = w * w; }
+      else if (j == 2) { o = f.W3; c = w * n_out; } else { o = f.Winv; c = nz * nz; }
+    } else if (!bwd) {
+      if (j == 0) { o = f.W; c = nz * nz; } else if (j == 1) { o = f.W1; c = half * w; }
+      else if (j == 2) { o = f.W2; c = w * w; } else { o = f.W3; c = w * n_out; }
+    } else {
+      if (j == 0) { o = f.W3T; c = w * n_out; } else if (j == 1) { o = f.W2T; c = w * w; }
+      else if (j == 2) { o = f.W1T; c = half * w; } else { o = f.WT; c = nz * nz; }
+    }
+    off = (size_t)L * f.step_floats + o;
+    n = c;
+  }
+  __device__ __forceinline__ int vec_layer(int idx) const {
+    if (inverse) return depth - 1 - idx;
+    return idx < depth ? idx : 2 * depth - 1 - idx;
+  }
+  __device__ __forceinline__ void issue_mat(int idx) {
+    if (idx >= n_mat) return;
+    size_t off; uint32_t n;
+    mat_item(idx, off, n);
+    f_bulk_load(f_smem_u32(mbuf[idx & 1]), params + off, n * 4u, mbar[idx & 1]);
+  }
+  __device__ __forceinline__ void issue_vec(int idx) {
+    if (idx >= n_vec) return;
+    f_bulk_load(f_smem_u32(vbuf[idx & 1]), params + (size_t)vec_layer(idx) * f.step_floats, (uint32_t)f.vec_floats * 4u,
+                vbar[idx & 1]);
+  }
+  // Returns the staged matrix of the current item and starts fetching the next one into the other buffer (free:
+  // its last reader finished before the __syncthreads that ends every mat-vec).
+  __device__ __forceinline__ const float* next_mat() {
+    const uint32_t i = m++;
+    f_mbar_wait(mbar[i & 1], (i >> 1) & 1u);
+    if (threadIdx.x == 0) issue_mat((int)i + 1);
+    return mbuf[i & 1];
+  }
+  __device__ __forceinline__ const float* next_vec() {
+    const uint32_t i = v++;
+    f_mbar_wait(vbar[i & 1], (i >> 1) & 1u);
+    if (threadIdx.x == 0) issue_vec((int)i + 1);
+    return vbuf[i & 1];
+  }
+};
+
+// carve the dynamic shared memory; returns the first free float
+__device__ __forceinline__ float* feeder_init(Feeder& fd, float* sm, const FlowArgs& a, bool with_bwd, bool inverse) {
+  const FlowLayout& f = a.fl;
+  fd.params = a.params; fd.f = f; fd.depth = a.depth; fd.perm2 = a.permutation == 2;
+  fd.with_bwd = with_bwd; fd.inverse = inverse;
+  fd.ipl = fd.perm2 ? 4 : 3;
+  fd.n_mat = a.depth * fd.ipl * ((with_bwd && !inverse) ? 2 : 1);
+  fd.n_vec = a.depth * ((with_bwd && !inverse) ? 2 : 1);
+  fd.m = fd.v = 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);   // 4 mbarriers (the buffer is 16-byte aligned)
+  float* p = sm + 8;
+  fd.vbuf[0] = p; p += f.vec_floats;
+  fd.vbuf[1] = p; p += f.vec_floats;
+  fd.mbuf[0] = p; p += f.max_mat;
+  fd.mbuf[1] = p; p += f.max_mat;
+  for (int i = 0; i < 2; ++i) { fd.mbar[i] = f_smem_u32(bars + i); fd.vbar[i] = f_smem_u32(bars + 2 + i); }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f_smem_u32(bars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { fd.issue_vec(0); fd.issue_mat(0); }
+  return p;
+}
+
+// out[s][j] = epi(s, j, sum_k in[s][k] * M[k*N + j]) for s < S, j < N.  M is row-major [K][N] in SHARED memory
+// (conflict-free along j); `in` lives in shared memory.  The K range is split across 256/Nr thread groups whose
+// partial sums meet in `scratch`.
 template <int S, class Epi>
-__device__ __forceinline__ void matvec(const float* __restrict__ M, int K, int N, const float* in, int ldin,
-                                       float* scratch, Epi epi) {
+__device__ __forceinline__ void matvec(const float* M, int K, int N, const float* in, int ldin, float* scratch,
+                                       Epi epi) {
   const int Nr = (N + 31) & ~31;
   const int G = FLOW_THREADS / Nr > 0 ? FLOW_THREADS / Nr : 1;
   const int tid = threadIdx.x;
@@ -41,7 +155,7 @@ __device__ __forceinline__ void matvec(const float* __restrict__ M, int K, int N
       const float* m = M + (size_t)k0 * N + j;
 #pragma unroll 8
       for (int k = k0; k < k1; ++k, m += N) {
-        const float w = __ldg(m);
+        const float w = *m;
 #pragma unroll
         for (int s = 0; s < S; ++s) acc[s] = fmaf(in[s * ldin + k], w, acc[s]);
       }
@@ -61,7 +175,7 @@ __device__ __forceinline__ void matvec(const float* __restrict__ M, int K, int N
   }
 }
 
-// sum over the threads of the CTA of one value per sample slot; result valid in thread 0.. (returned to all)
+// sum over the threads of the CTA of one value per sample slot (warp shuffles, then one shared-memory pass)
 template <int S>
 __device__ __forceinline__ void block_sum(float (&v)[S], float* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,16 +197,17 @@ __device__ __forceinline__ void block_sum(float (&v)[S], float* red) {
 
 template <int S>
 __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const FlowLayout& f = a.fl;
   const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
   const int nmax = max(nz, max(w, n_out));
   const int nr_max = (nmax + 31) & ~31;
   const int stash_step = 2 * w + nz;  // a1[w], a2[w], scale[half], x2+shift[half]
-  float* cur = sm;                         // [S][nz]
+  Feeder fd;
+  float* cur = feeder_init(fd, sm, a, a.grad != nullptr, false);   // [S][nz]
   float* ta = cur + S * nz;                // [S][nmax]
   float* tb = ta + S * nmax;               // [S][nmax]
-  float* scratch = tb + S * nmax;          // [256/32*... ] partial sums: G*S*Nr <= 256*S (+ slack)
+  float* scratch = tb + S * nmax;          // partial sums: G*S*Nr <= 256*S
   float* red = scratch + S * max(FLOW_THREADS, nr_max);
   float* stash = red + (FLOW_THREADS / 32) * S;  // [depth][S][stash_step]
   const int tid = threadIdx.x;
@@ -110,7 +225,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
   for (int s = 0; s < S; ++s) ld[s] = 0.f;
 
   for (int L = 0; L < a.depth; ++L) {
-    const float* P = a.params + (size_t)L * f.step_floats;
+    const float* P = fd.next_vec();   // this step's vectors, in shared memory
     float* st = stash + (size_t)L * S * stash_step;
     // actnorm (model.py:282-284): (x + b) * exp(3 logs)
     for (int i = tid; i < S * nz; i += FLOW_THREADS) {
@@ -119,7 +234,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
     }
     __syncthreads();
     if (a.permutation == 2) {   // model.py:187: z @ W
-      matvec<S>(P + f.W, nz, nz, ta, nmax, scratch, [&](int s, int j, float v) { cur[s * nz + j] = v; });
+      matvec<S>(fd.next_mat(), nz, nz, ta, nmax, scratch, [&](int s, int j, float v) { cur[s * nz + j] = v; });
     } else {                    // intended shuffle_features: h[:, idx]
       const int* idx = reinterpret_cast<const int*>(P + f.perm);
       for (int i = tid; i < S * nz; i += FLOW_THREADS) cur[i] = ta[(i / nz) * nmax + idx[i % nz]];
@@ -134,11 +249,11 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
     float* a2 = st + S * w;     // [S][w]
     float* sc = a2 + S * w;     // [S][half]
     float* xs = sc + S * half;  // [S][half]
-    matvec<S>(P + f.W1, half, w, cur, nz, scratch,
+    matvec<S>(fd.next_mat(), half, w, cur, nz, scratch,
               [&](int s, int j, float v) { a1[s * w + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
-    matvec<S>(P + f.W2, w, w, a1, w, scratch,
+    matvec<S>(fd.next_mat(), w, w, a1, w, scratch,
               [&](int s, int j, float v) { a2[s * w + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
-    matvec<S>(P + f.W3, w, n_out, a2, w, scratch,
+    matvec<S>(fd.next_mat(), w, n_out, a2, w, scratch,
               [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
     if (a.coupling == 1) {      // model.py:410-418
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
@@ -191,7 +306,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
   // ---- analytic backward of -sum_b ll_b: seed g = z_out, d/dlogdet = -1 ----
   float* g = cur;  // in place
   for (int L = a.depth - 1; L >= 0; --L) {
-    const float* P = a.params + (size_t)L * f.step_floats;
+    const float* P = fd.next_vec();
     float* st = stash + (size_t)L * S * stash_step;
     const float* a1 = st;
     const float* a2 = st + S * w;
@@ -215,15 +330,15 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
       }
     }
     __syncthreads();
-    matvec<S>(P + f.W3T, n_out, w, ta, nmax, scratch,
+    matvec<S>(fd.next_mat(), n_out, w, ta, nmax, scratch,
               [&](int s, int j, float v) { tb[s * nmax + j] = a2[s * w + j] > 0.f ? v * P[f.e2 + j] : 0.f; });
-    matvec<S>(P + f.W2T, w, w, tb, nmax, scratch,
+    matvec<S>(fd.next_mat(), w, w, tb, nmax, scratch,
               [&](int s, int j, float v) { ta[s * nmax + j] = a1[s * w + j] > 0.f ? v * P[f.e1 + j] : 0.f; });
-    matvec<S>(P + f.W1T, w, half, ta, nmax, scratch, [&](int s, int j, float v) { g[s * nz + j] += v; });
+    matvec<S>(fd.next_mat(), w, half, ta, nmax, scratch, [&](int s, int j, float v) { g[s * nz + j] += v; });
     if (a.permutation == 2) {   // g @ W^T, then the actnorm scale
       for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[(i / nz) * nmax + i % nz] = g[i];
       __syncthreads();
-      matvec<S>(P + f.WT, nz, nz, ta, nmax, scratch,
+      matvec<S>(fd.next_mat(), nz, nz, ta, nmax, scratch,
                 [&](int s, int j, float v) { g[s * nz + j] = v * P[f.an_e + j]; });
     } else {
       const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
@@ -245,12 +360,13 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
 // reverse pass (model.py:424-456, :361-363, :484-498)
 template <int S>
 __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const FlowLayout& f = a.fl;
   const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
   const int nmax = max(nz, max(w, n_out));
   const int nr_max = (nmax + 31) & ~31;
-  float* cur = sm;
+  Feeder fd;
+  float* cur = feeder_init(fd, sm, a, false, true);
   float* ta = cur + S * nz;
   float* tb = ta + S * nmax;
   float* scratch = tb + S * nmax;
@@ -267,12 +383,12 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
 #pragma unroll
   for (int s = 0; s < S; ++s) ld[s] = 0.f;
   for (int L = a.depth - 1; L >= 0; --L) {
-    const float* P = a.params + (size_t)L * f.step_floats;
-    matvec<S>(P + f.W1, half, w, cur, nz, scratch,
+    const float* P = fd.next_vec();
+    matvec<S>(fd.next_mat(), half, w, cur, nz, scratch,
               [&](int s, int j, float v) { ta[s * nmax + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
-    matvec<S>(P + f.W2, w, w, ta, nmax, scratch,
+    matvec<S>(fd.next_mat(), w, w, ta, nmax, scratch,
               [&](int s, int j, float v) { tb[s * nmax + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
-    matvec<S>(P + f.W3, w, n_out, tb, nmax, scratch,
+    matvec<S>(fd.next_mat(), w, n_out, tb, nmax, scratch,
               [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
     if (a.coupling == 1) {      // model.py:432-438
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
@@ -293,7 +409,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
     for (int i = tid; i < S * nz; i += FLOW_THREADS) tb[(i / nz) * nmax + i % nz] = cur[i];
     __syncthreads();
     if (a.permutation == 2) {   // model.py:193-196: z @ inverse(W), then actnorm reverse (:288-291)
-      matvec<S>(P + f.Winv, nz, nz, tb, nmax, scratch,
+      matvec<S>(fd.next_mat(), nz, nz, tb, nmax, scratch,
                 [&](int s, int j, float v) { cur[s * nz + j] = v * P[f.an_ei + j] - P[f.an_b + j]; });
     } else {
       const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
@@ -307,6 +423,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
 #pragma unroll
       for (int s = 0; s < S; ++s) ld[s] -= P[f.ld_const + 1], ld[s] -= P[f.ld_const];
     }
+    __syncthreads();   // every read of this step's vector block is done before its buffer is refilled
   }
   block_sum<S>(ld, red);
   if (tid == 0 && a.logdet) {
@@ -398,17 +515,20 @@ int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t*
   return LSNF_OK;
 }
 
+// samples per CTA: every CTA streams all the parameters (~1.3 MB per pass) through its shared memory, so a few
+// samples share one stream; 4 keeps the reference batch of 100 on 25 SMs for ~20 us
 static int pick_s(int B) {
-  if (B <= 160) return 1;
-  if (B <= 600) return 2;
-  if (B <= 2400) return 4;
+  if (B <= 32) return 1;
+  if (B <= 64) return 2;
+  if (B <= 1200) return 4;
   return 8;
 }
 
 static size_t flow_smem_floats(const FlowLayout& f, int S, int depth, bool stash) {
   const int nmax = std::max(f.nz, std::max(f.w, f.n_out));
   const int nr_max = (nmax + 31) & ~31;
-  size_t n = (size_t)S * f.nz + 2 * (size_t)S * nmax + (size_t)S * std::max(FLOW_THREADS, nr_max) +
+  size_t n = 8 + 2 * f.vec_floats + 2 * f.max_mat +   // mbarriers, staged vector blocks and matrices
+             (size_t)S * f.nz + 2 * (size_t)S * nmax + (size_t)S * std::max(FLOW_THREADS, nr_max) +
              (size_t)(FLOW_THREADS / 32) * S;
   if (stash) n += (size_t)depth * S * (2 * f.w + f.nz);
   return n;
@@ -446,7 +566,7 @@ int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, flo
   a.in = z; a.z_out = z_out; a.logdet = logdet; a.logp = logp; a.grad = grad_z;
   const int S = pick_s(a.B);
   const size_t smem = flow_smem_floats(a.fl, S, a.depth, true) * 4;
-  if (smem > 220 * 1024) { set_error("flow kernel shared memory budget exceeded"); return LSNF_ERR_INVALID; }
+  if (smem > 227 * 1024) { set_error("flow kernel shared memory budget exceeded"); return LSNF_ERR_INVALID; }
   switch (S) {
     case 1: return launch_fwd_t<1>(a, smem, s);
     case 2: return launch_fwd_t<2>(a, smem, s);

@@ -163,36 +163,54 @@ int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s) {
 // written directly as the im2col operand of the last layer's data gradient:
 //   A[b][iy][ix][tap*nc + c] = g[b][c][iy*s - p + ky][ix*s - p + kx]  (0 outside the image), 64 columns.
 // ---------------------------------------------------------------------------------------------------
-__global__ void recon_grad_im2col_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
-                                         __nv_bfloat16* __restrict__ a, int B, int nc, int img, int hin, int k,
-                                         int s, int p, float inv_sigma2) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * hin * hin * BLOCK_K;
-  if (i >= total) return;
-  const int col = (int)(i % BLOCK_K);
-  const long long row = i / BLOCK_K;
-  const int ix = (int)(row % hin), iy = (int)((row / hin) % hin), b = (int)(row / ((long long)hin * hin));
-  float v = 0.f;
-  if (col < k * k * nc) {
-    const int tap = col / nc, c = col % nc;
-    const int oy = iy * s - p + tap / k, ox = ix * s - p + tap % k;
+// One CTA per (sample, input row, segment of <= 32 input columns): the loss-gradient values the segment's taps touch
+// are computed once into shared memory (coalesced reads of x_hat and x), then written out as 64-column im2col rows
+// (coalesced 2-byte stores).
+constexpr int IM2COL_SEG = 32;
+__global__ void __launch_bounds__(128) recon_grad_im2col_kernel(const float* __restrict__ xhat,
+                                                                const float* __restrict__ x,
+                                                                uint16_t* __restrict__ a, int B, int nc, int img,
+                                                                int hin, int k, int s, int p, float inv_sigma2) {
+  extern __shared__ float g[];   // [nc][k][span], span = (seg-1)*s + k
+  const int segs = (hin + IM2COL_SEG - 1) / IM2COL_SEG;
+  const int seg = blockIdx.x % segs, iy = (blockIdx.x / segs) % hin, b = blockIdx.x / (segs * hin);
+  const int ix0 = seg * IM2COL_SEG, nseg = min(IM2COL_SEG, hin - ix0);
+  const int span = (nseg - 1) * s + k;
+  const int oy0 = iy * s - p, ox0 = ix0 * s - p;
+  for (int i = threadIdx.x; i < nc * k * span; i += blockDim.x) {
+    const int xx = i % span, ky = (i / span) % k, c = i / (span * k);
+    const int oy = oy0 + ky, ox = ox0 + xx;
+    float v = 0.f;
     if (oy >= 0 && oy < img && ox >= 0 && ox < img) {
       const size_t o = (((size_t)b * nc + c) * img + oy) * img + ox;
       const float xh = xhat[o];
       v = (xh - x[o]) * inv_sigma2 * (1.f - xh * xh);
     }
+    g[i] = v;
   }
-  __nv_bfloat16 hi, lo;
-  split_bf16(v, hi, lo);
-  a[row * 2 * BLOCK_K + col] = hi;
-  a[row * 2 * BLOCK_K + BLOCK_K + col] = lo;
+  __syncthreads();
+  const size_t row0 = ((size_t)b * hin + iy) * hin + ix0;
+  for (int i = threadIdx.x; i < nseg * BLOCK_K; i += blockDim.x) {
+    const int col = i % BLOCK_K, r = i / BLOCK_K;
+    float v = 0.f;
+    if (col < k * k * nc) {
+      const int tap = col / nc, c = col % nc;
+      v = g[(c * k + tap / k) * span + r * s + tap % k];
+    }
+    uint16_t hi, lo;
+    split16(v, false, hi, lo);   // bf16: operand of the data-gradient stages
+    a[(row0 + r) * 2 * BLOCK_K + col] = hi;
+    a[(row0 + r) * 2 * BLOCK_K + BLOCK_K + col] = lo;
+  }
 }
 
 int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s) {
   const auto& y = plan->layers[plan->n_layers - 1];
-  const long long total = (long long)plan->cfg.batch * y.hin * y.hin * BLOCK_K;
-  recon_grad_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      (const float*)(plan->ws + plan->off_xhat), x, (__nv_bfloat16*)(plan->ws + plan->off_im2col), plan->cfg.batch,
+  const int segs = (y.hin + IM2COL_SEG - 1) / IM2COL_SEG;
+  const int span = (std::min(IM2COL_SEG, y.hin) - 1) * y.s + y.k;
+  const size_t smem = (size_t)plan->cfg.nc * y.k * span * 4;
+  recon_grad_im2col_kernel<<<plan->cfg.batch * y.hin * segs, 128, smem, s>>>(
+      (const float*)(plan->ws + plan->off_xhat), x, (uint16_t*)(plan->ws + plan->off_im2col), plan->cfg.batch,
       plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p, 1.f / (sigma * sigma));
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;

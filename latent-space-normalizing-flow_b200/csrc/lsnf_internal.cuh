@@ -78,6 +78,8 @@ struct FlowLayout {
   int nz, w, n_out, half;
   size_t an_b, an_e, an_ei, W, WT, Winv, W1, W1T, b1, e1, W2, W2T, b2, e2, W3, W3T, b3, e3, perm, perm_inv, ld_const;
   size_t step_floats;
+  size_t vec_floats;  // the per-step vectors come first in a step's block, [0, vec_floats)
+  size_t max_mat;     // floats of the largest matrix
 };
 
 }  // namespace lsnf

@@ -187,12 +187,16 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
     f.nz = c.nz; f.w = c.f_width; f.half = c.nz / 2; f.n_out = c.f_coupling ? c.nz : c.nz / 2;
     size_t o = 0;
     auto tk = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
+    // vectors first (they are staged into shared memory as one block), then the matrices
     f.an_b = tk(f.nz); f.an_e = tk(f.nz); f.an_ei = tk(f.nz);
-    f.W = tk((size_t)f.nz * f.nz); f.WT = tk((size_t)f.nz * f.nz); f.Winv = tk((size_t)f.nz * f.nz);
-    f.W1 = tk((size_t)f.half * f.w); f.W1T = tk((size_t)f.half * f.w); f.b1 = tk(f.w); f.e1 = tk(f.w);
-    f.W2 = tk((size_t)f.w * f.w); f.W2T = tk((size_t)f.w * f.w); f.b2 = tk(f.w); f.e2 = tk(f.w);
-    f.W3 = tk((size_t)f.w * f.n_out); f.W3T = tk((size_t)f.w * f.n_out); f.b3 = tk(f.n_out); f.e3 = tk(f.n_out);
+    f.b1 = tk(f.w); f.e1 = tk(f.w); f.b2 = tk(f.w); f.e2 = tk(f.w); f.b3 = tk(f.n_out); f.e3 = tk(f.n_out);
     f.perm = tk(f.nz); f.perm_inv = tk(f.nz); f.ld_const = tk(4);
+    f.vec_floats = o;
+    f.W = tk((size_t)f.nz * f.nz); f.WT = tk((size_t)f.nz * f.nz); f.Winv = tk((size_t)f.nz * f.nz);
+    f.W1 = tk((size_t)f.half * f.w); f.W1T = tk((size_t)f.half * f.w);
+    f.W2 = tk((size_t)f.w * f.w); f.W2T = tk((size_t)f.w * f.w);
+    f.W3 = tk((size_t)f.w * f.n_out); f.W3T = tk((size_t)f.w * f.n_out);
+    f.max_mat = std::max({(size_t)f.nz * f.nz, (size_t)f.half * f.w, (size_t)f.w * f.w, (size_t)f.w * f.n_out});
     f.step_floats = o;
     p->off_flow = take(f.step_floats * 4 * c.f_depth);
   }
@@ -582,27 +586,77 @@ extern "C" int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps) 
 }
 
 // the g_l_steps loop on stream s: inputs are the workspace copies of z and x
+// LSNF_TRACE=1: time every launch of the second iteration in situ with CUDA events and print the table to stderr
+struct LoopTrace {
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> name;
+  cudaStream_t s;
+  bool on = false;
+  void mark(const char* n) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    name.push_back(n);
+  }
+  void report() {
+    if (!on || ev.empty()) return;
+    cudaEventSynchronize(ev.back());
+    float total = 0.f;
+    cudaEventElapsedTime(&total, ev.front(), ev.back());
+    fprintf(stderr, "[lsnf trace] one Langevin iteration: %.1f us\n", total * 1e3f);
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "[lsnf trace]   %-28s %8.1f us\n", name[i].c_str(), ms * 1e3f);
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    name.clear();
+  }
+};
+
 static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_size, float sigma, int with_noise,
                          const float* eps, uint64_t seed, uint64_t sample_offset, const uint64_t* dyn, float* gnorms,
                          cudaStream_t s) {
   int rc;
+  static int trace_env = -1;
+  if (trace_env < 0) { const char* e = getenv("LSNF_TRACE"); trace_env = (e && e[0] == '1') ? 1 : 0; }
+  LoopTrace tr;
+  tr.s = s;
   const lsnf_config& c = plan->cfg;
   float* z = (float*)(plan->ws + plan->off_z);
   float* gf = (float*)(plan->ws + plan->off_gradf);
   const float* partial = (const float*)(plan->ws + plan->off_partial);
   for (int t = 0; t < steps; ++t) {
+    tr.on = trace_env == 1 && t == 1 && !dyn;
+    tr.mark("start");
     // fork: the flow prior (train.py:316-323) only needs z; it overlaps the generator stages on the side stream
     LSNF_CUDA(cudaEventRecord(plan->ev_fork, s));
     LSNF_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
     if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, plan->side))) return rc;
     LSNF_CUDA(cudaEventRecord(plan->ev_join, plan->side));
-    if ((rc = gen_forward(plan, z, nullptr, s, false))) return rc;
-    if ((rc = gen_dgrad_partial(plan, x, sigma, s))) return rc;
+    for (int l = 0; l < plan->n_layers; ++l) {
+      if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
+      tr.mark(("forward layer " + std::to_string(l)).c_str());
+    }
+    if ((rc = launch_last_gather(plan, s))) return rc;
+    tr.mark("gather + tanh");
+    if ((rc = launch_recon_grad_im2col(plan, x, sigma, s))) return rc;
+    tr.mark("recon grad + im2col");
+    for (int i = plan->n_layers; i < 2 * plan->n_layers; ++i) {
+      if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+      tr.mark(("dgrad layer " + std::to_string(plan->stages[i].layer)).c_str());
+    }
     LSNF_CUDA(cudaStreamWaitEvent(s, plan->ev_join, 0));
+    tr.mark("join flow prior");
     const float* e = eps ? eps + (size_t)t * c.batch * c.nz : nullptr;
     if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gf, step_size, e, with_noise, seed,
                             sample_offset, (uint32_t)t, dyn, t == steps - 1 ? gnorms : nullptr, 1, s)))
       return rc;
+    tr.mark("update");
+    tr.report();
   }
   return LSNF_OK;
 }
