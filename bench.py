@@ -113,7 +113,7 @@ def build_models(w, device):
     return args, netG, netF, gsd, fsd
 
 
-def cpu_oracle_rate(w, gsd, fsd, langevin_steps, repeats=1, threads=None):
+def cpu_oracle_rate(w, gsd, fsd, langevin_steps, repeats=1, threads=None, min_seconds=None):
     """latent-steps/s of the CPU oracle (restatement of the reference's torch path) on the host cores."""
     from oracle import refpath
     from lsnf_b200 import synth
@@ -125,12 +125,21 @@ def cpu_oracle_rate(w, gsd, fsd, langevin_steps, repeats=1, threads=None):
     x, z0, eps = synth.inputs(w["B"], w["nz"], 3, w["img"], langevin_steps, seed=1)
     x, z0, eps = torch.from_numpy(x), torch.from_numpy(z0), torch.from_numpy(eps)
     refpath.langevin(z0, x, gp, fp, layers, depth=5, steps=1, step_size=0.1, sigma=w["sigma"], eps=eps)  # warm-up
+    if min_seconds:
+        # bounded sample: repeat chunks of `langevin_steps` iterations until about min_seconds of CPU work is done
+        done, t0 = 0, time.perf_counter()
+        while True:
+            refpath.langevin(z0, x, gp, fp, layers, depth=5, steps=langevin_steps, step_size=0.1, sigma=w["sigma"], eps=eps)
+            done += langevin_steps
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds or done >= 400:
+                return w["B"] * done / dt, dt, threads, done
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
         refpath.langevin(z0, x, gp, fp, layers, depth=5, steps=langevin_steps, step_size=0.1, sigma=w["sigma"], eps=eps)
         best = min(best, time.perf_counter() - t0)
-    return w["B"] * langevin_steps / best, best, threads
+    return w["B"] * langevin_steps / best, best, threads, langevin_steps
 
 
 def cpu_model():
@@ -151,13 +160,13 @@ def run_reference(a, w, rank):
     from lsnf_b200 import synth
     gsd = synth.generator_state(w["dataset"], w["nz"], w["ngf"], 3, seed=1)
     fsd = synth.flow_state(w["nz"], w["f_width"], 5, 1, 2, seed=1)
-    sample_T = {"svhn": 4, "cifar10": 1, "celeba_crop": 1, "celeba_hq256": 1}[a.workload]
+    sample_T = {"svhn": 20, "cifar10": 4, "celeba_crop": 4, "celeba_hq256": 2}[a.workload]
     for _ in range(max(a.warmup, 1) - 1):
         cpu_oracle_rate(w, gsd, fsd, 1)
     t0 = time.perf_counter()
     total = 0.0
     for _ in range(a.steps):
-        rate, dt, threads = cpu_oracle_rate(w, gsd, fsd, sample_T)
+        rate, dt, threads, _ = cpu_oracle_rate(w, gsd, fsd, sample_T)
         total += dt
     value = w["B"] * sample_T * a.steps / total
     sample = f"{sample_T} Langevin iteration(s) of B={w['B']} per step (per-iteration cost does not depend on T)"
@@ -213,7 +222,10 @@ def main():
     norms = torch.zeros(2, device=dev)
     sample_offset = rank * B
 
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
+
     def step(i):
+        flush.zero_()   # L2 flush between timed steps (inside the timed region: ~0.05 ms per step)
         plan.langevin_run(z0, x, T, 0.1, w["sigma"], with_noise=True, eps=None, seed=1234 + i,
                           sample_offset=sample_offset, out=out, norms=norms)
 
@@ -298,27 +310,50 @@ def main():
         table.append(dict(stage=idx, kind="fwd" if info.kind == 0 else "dgrad", layer=info.layer, us=us,
                           alg_gflop=alg / 1e9, nominal_gflop=info.flops / 1e9, tflops_alg=alg / us / 1e6,
                           block_n=info.block_n, k_splits=info.k_splits))
+    # the flow-prior kernel alone (it overlaps the generator stages inside the loop)
+    zf = torch.from_numpy(z0_np).to(dev).reshape(B, nz).contiguous()
+    for _ in range(2):
+        plan.flow_forward(zf, want_grad=True)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(reps):
+        plan.flow_forward(zf, want_grad=True)
+    s1.record()
+    torch.cuda.synchronize()
+    flow_us = s0.elapsed_time(s1) * 1e3 / reps
     gemm_us = sum(t["us"] for t in table)
     dom = max(table, key=lambda t: t["us"])
     step_us = ms_total * 1e3 / a.steps / T   # one Langevin iteration
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
+    if os.path.exists(tpath):
+        try:
+            td = json.load(open(tpath))
+            if td.get("workload") == a.workload and td.get("stage") == dom["stage"]:
+                traffic = td.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    kname = "tapgemm_tc2_kernel (CTA pair, N tile 256)" if dom["block_n"] == 256 else f"tapgemm_tc_kernel<{dom['block_n']}>"
     roofline = {"bound": "tensor", "achieved": dom["tflops_alg"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": dom["tflops_alg"] / pk["tflops"], "traffic": None,
-                "kernel": f"tapgemm_tc_kernel<{dom['block_n']}> stage {dom['stage']} ({dom['kind']} layer {dom['layer']})",
+                "frac": dom["tflops_alg"] / pk["tflops"], "traffic": traffic,
+                "kernel": f"{kname} stage {dom['stage']} ({dom['kind']} layer {dom['layer']})",
                 "kernel_us": dom["us"], "alg_gflop_per_launch": dom["alg_gflop"],
                 "peak_source": pk["src"] + ", burst bf16 (kernel timed alone)",
                 "mma": "tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulate), 3 passes (hi*hi + hi*lo + lo*hi); "
                        "algorithmic FLOPs count one pass",
-                "share_of_iteration": dom["us"] / step_us, "all_gemm_stages_us": gemm_us, "iteration_us": step_us}
+                "share_of_iteration": dom["us"] / step_us, "all_gemm_stages_us": gemm_us, "iteration_us": step_us,
+                "flow_prior_kernel_us": flow_us}
     if a.stage_table:
-        json.dump(table, open(a.stage_table, "w"), indent=1)
+        json.dump({"stages": table, "flow_prior_kernel_us": flow_us, "iteration_us": step_us}, open(a.stage_table, "w"), indent=1)
 
     cpu_b = None
     if not a.no_cpu_baseline:
-        cpu_T = {"svhn": 8, "cifar10": 3, "celeba_crop": 4, "celeba_hq256": 3}[a.workload]
-        rate, dt, threads = cpu_oracle_rate(w, gsd, fsd, cpu_T)
+        cpu_T = {"svhn": 10, "cifar10": 2, "celeba_crop": 2, "celeba_hq256": 1}[a.workload]
+        rate, dt, threads, done = cpu_oracle_rate(w, gsd, fsd, cpu_T, min_seconds=12.0)
         cpu_b = {"value": rate, "unit": "latent-steps/s", "cores": threads, "kind": "port",
-                 "sample": f"{cpu_T} Langevin iterations of the same B={B} workload in {dt:.1f} s on {cpu_model()} "
-                           f"(oracle/refpath.py, torch CPU fp32)"}
+                 "sample": f"{done} Langevin iterations of the same B={B} workload in {dt:.1f} s on {cpu_model()} "
+                           f"({threads} threads; oracle/refpath.py, torch CPU fp32)"}
 
     alg_per_ls = 2 * sum(exact) + flow_flops(nz, w["f_width"])
     line = {
@@ -327,7 +362,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split/f32-accumulate", "data": "synthetic",
         "config": {"workload": a.workload, "dataset": w["dataset"], "nz": nz, "ngf": w["ngf"], "f_width": w["f_width"],
                    "g_l_steps": T, "batch_per_gpu": B, "g_llhd_sigma": w["sigma"], "noise": "in-kernel Philox4x32-10",
-                   "l2": f"no flush: per-call working set {plan.ws_bytes / 1e6:.0f} MB > 126 MB L2",
+                   "l2": f"flushed between timed steps (256 MB written, inside the timed region); per-call working set "
+                         f"{plan.ws_bytes / 1e6:.0f} MB",
                    "alg_gflop_per_latent_step": alg_per_ls / 1e9,
                    "frac_of_tensor_roofline": value / world / (pk["tflops_sustained"] * 1e12 / alg_per_ls),
                    "roofline_denominator": f"{pk['tflops_sustained']} TFLOP/s bf16 sustained, {pk['src']}"},

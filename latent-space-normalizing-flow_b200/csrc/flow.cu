@@ -17,6 +17,7 @@ struct FlowArgs {
   float* logdet;        // forward: logdet; inverse: -objective
   float* logp;
   float* grad;
+  uint32_t ring_floats;  // shared-memory ring that streams the matrices
 };
 
 constexpr int FLOW_THREADS = 256;
@@ -46,14 +47,24 @@ __device__ __forceinline__ void f_bulk_load(uint32_t dst, const float* src, uint
                : "memory");
 }
 
+constexpr int FEED_SLOTS = 8;   // matrices that may be in flight at once (mbarrier slots)
+
+// Streams the matrices of the whole pass through a shared-memory byte ring: thread 0 keeps issuing bulk copies for
+// as many upcoming matrices as fit (typically 4-6 in flight, > 100 KB), so the mat-vec chain is bound by one SM's
+// L2 bandwidth instead of by the latency of one copy per step.  Space is reclaimed in FIFO order when the mat-vec
+// that used it has passed its closing __syncthreads.
 struct Feeder {
   const float* params;
   FlowLayout f;
-  int depth, perm2, with_bwd, inverse;
-  float* mbuf[2];
-  float* vbuf[2];
-  uint32_t mbar[2], vbar[2];
+  int depth, perm2, inverse;
+  float* ring;            // [ring_floats]
+  float* vbuf[2];         // the per-step vector blocks, double-buffered
+  uint32_t* item_off;     // [FEED_SLOTS] placement of each in-flight matrix (floats from `ring`)
+  uint32_t* item_fp;      // [FEED_SLOTS] footprint incl. wrap waste
+  uint32_t bar0, vbar0;   // shared addresses of the mbarrier arrays
+  uint32_t ring_floats;
   uint32_t m, v;          // next matrix / vector-block item to be consumed
+  uint32_t next_issue, head, used;   // producer state (meaningful in thread 0 only)
   int n_mat, n_vec, ipl;  // items in the whole launch, matrices per step
 
   // matrix item -> (offset, floats).  forward pass: per step [W] W1 W2 W3; backward: per step (descending) W3T W2T
@@ -83,28 +94,48 @@ struct Feeder {
     if (inverse) return depth - 1 - idx;
     return idx < depth ? idx : 2 * depth - 1 - idx;
   }
-  __device__ __forceinline__ void issue_mat(int idx) {
-    if (idx >= n_mat) return;
-    size_t off; uint32_t n;
-    mat_item(idx, off, n);
-    f_bulk_load(f_smem_u32(mbuf[idx & 1]), params + off, n * 4u, mbar[idx & 1]);
+  // thread 0: issue every upcoming matrix that fits into the ring (FIFO allocation with wrap-around)
+  __device__ __forceinline__ void pump(uint32_t consumer) {
+    while ((int)next_issue < n_mat && next_issue < consumer + FEED_SLOTS - 1) {
+      size_t off; uint32_t n;
+      mat_item((int)next_issue, off, n);
+      uint32_t place, fp;
+      if (used == 0) head = 0;   // empty ring: restart at the beginning (guarantees progress when ring < 2 matrices)
+      if (head + n > ring_floats) {
+        const uint32_t waste = ring_floats - head;
+        if (used + waste + n > ring_floats) break;
+        place = 0; fp = waste + n; head = n;
+      } else {
+        if (used + n > ring_floats) break;
+        place = head; fp = n; head += n;
+      }
+      const uint32_t slot = next_issue % FEED_SLOTS;
+      item_off[slot] = place; item_fp[slot] = fp;
+      used += fp;
+      f_bulk_load(f_smem_u32(ring + place), params + off, n * 4u, bar0 + 8u * slot);
+      ++next_issue;
+    }
   }
   __device__ __forceinline__ void issue_vec(int idx) {
     if (idx >= n_vec) return;
     f_bulk_load(f_smem_u32(vbuf[idx & 1]), params + (size_t)vec_layer(idx) * f.step_floats, (uint32_t)f.vec_floats * 4u,
-                vbar[idx & 1]);
+                vbar0 + 8u * (idx & 1));
   }
-  // Returns the staged matrix of the current item and starts fetching the next one into the other buffer (free:
-  // its last reader finished before the __syncthreads that ends every mat-vec).
+  // Returns the staged matrix of the current item.  The previous item's space is reclaimed here: its mat-vec has
+  // passed its closing __syncthreads, so no thread reads it any more.
   __device__ __forceinline__ const float* next_mat() {
     const uint32_t i = m++;
-    f_mbar_wait(mbar[i & 1], (i >> 1) & 1u);
-    if (threadIdx.x == 0) issue_mat((int)i + 1);
-    return mbuf[i & 1];
+    if (threadIdx.x == 0) {
+      if (i > 0) used -= item_fp[(i - 1) % FEED_SLOTS];
+      pump(i);
+    }
+    const uint32_t slot = i % FEED_SLOTS;
+    f_mbar_wait(bar0 + 8u * slot, (i / FEED_SLOTS) & 1u);
+    return ring + item_off[slot];
   }
   __device__ __forceinline__ const float* next_vec() {
     const uint32_t i = v++;
-    f_mbar_wait(vbar[i & 1], (i >> 1) & 1u);
+    f_mbar_wait(vbar0 + 8u * (i & 1), (i >> 1) & 1u);
     if (threadIdx.x == 0) issue_vec((int)i + 1);
     return vbuf[i & 1];
   }
@@ -114,24 +145,29 @@ struct Feeder {
 __device__ __forceinline__ float* feeder_init(Feeder& fd, float* sm, const FlowArgs& a, bool with_bwd, bool inverse) {
   const FlowLayout& f = a.fl;
   fd.params = a.params; fd.f = f; fd.depth = a.depth; fd.perm2 = a.permutation == 2;
-  fd.with_bwd = with_bwd; fd.inverse = inverse;
+  fd.inverse = inverse;
   fd.ipl = fd.perm2 ? 4 : 3;
   fd.n_mat = a.depth * fd.ipl * ((with_bwd && !inverse) ? 2 : 1);
   fd.n_vec = a.depth * ((with_bwd && !inverse) ? 2 : 1);
   fd.m = fd.v = 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);   // 4 mbarriers (the buffer is 16-byte aligned)
-  float* p = sm + 8;
+  fd.next_issue = fd.head = fd.used = 0;
+  fd.ring_floats = a.ring_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);   // FEED_SLOTS + 2 mbarriers (the buffer is 16-byte aligned)
+  fd.bar0 = f_smem_u32(bars);
+  fd.vbar0 = f_smem_u32(bars + FEED_SLOTS);
+  fd.item_off = reinterpret_cast<uint32_t*>(bars + FEED_SLOTS + 2);
+  fd.item_fp = fd.item_off + FEED_SLOTS;
+  float* p = sm + 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS;
   fd.vbuf[0] = p; p += f.vec_floats;
   fd.vbuf[1] = p; p += f.vec_floats;
-  fd.mbuf[0] = p; p += f.max_mat;
-  fd.mbuf[1] = p; p += f.max_mat;
-  for (int i = 0; i < 2; ++i) { fd.mbar[i] = f_smem_u32(bars + i); fd.vbar[i] = f_smem_u32(bars + 2 + i); }
+  fd.ring = p; p += a.ring_floats;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f_smem_u32(bars + i)));
+    for (int i = 0; i < FEED_SLOTS + 2; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f_smem_u32(bars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) { fd.issue_vec(0); fd.issue_mat(0); }
+  if (threadIdx.x == 0) { fd.issue_vec(0); fd.pump(0); }
   return p;
 }
 
@@ -524,14 +560,27 @@ static int pick_s(int B) {
   return 8;
 }
 
-static size_t flow_smem_floats(const FlowLayout& f, int S, int depth, bool stash) {
+// shared-memory floats besides the matrix ring
+static size_t flow_fixed_floats(const FlowLayout& f, int S, int depth, bool stash) {
   const int nmax = std::max(f.nz, std::max(f.w, f.n_out));
   const int nr_max = (nmax + 31) & ~31;
-  size_t n = 8 + 2 * f.vec_floats + 2 * f.max_mat +   // mbarriers, staged vector blocks and matrices
+  size_t n = 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS + 2 * f.vec_floats +   // mbarriers, ring bookkeeping, vector blocks
              (size_t)S * f.nz + 2 * (size_t)S * nmax + (size_t)S * std::max(FLOW_THREADS, nr_max) +
              (size_t)(FLOW_THREADS / 32) * S;
   if (stash) n += (size_t)depth * S * (2 * f.w + f.nz);
   return n;
+}
+
+// ring size: everything one pass streams if it fits, else whatever the 227 KB budget leaves (>= the largest matrix)
+static int flow_ring_floats(const FlowLayout& f, size_t fixed, int depth, bool both_passes, uint32_t* ring) {
+  const size_t budget = (size_t)227 * 1024 / 4;
+  if (fixed + f.max_mat > budget) return -1;
+  const size_t per_step = (size_t)f.nz * f.nz + (size_t)f.half * f.w + (size_t)f.w * f.w + (size_t)f.w * f.n_out;
+  const size_t want = per_step * depth * (both_passes ? 2 : 1);
+  size_t r = std::min(budget - fixed, want + 4);
+  r = std::max(r, f.max_mat) / 4 * 4;
+  *ring = (uint32_t)r;
+  return 0;
 }
 
 template <int S>
@@ -565,8 +614,12 @@ int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, flo
   a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
   a.in = z; a.z_out = z_out; a.logdet = logdet; a.logp = logp; a.grad = grad_z;
   const int S = pick_s(a.B);
-  const size_t smem = flow_smem_floats(a.fl, S, a.depth, true) * 4;
-  if (smem > 227 * 1024) { set_error("flow kernel shared memory budget exceeded"); return LSNF_ERR_INVALID; }
+  const size_t fixed = flow_fixed_floats(a.fl, S, a.depth, true);
+  if (flow_ring_floats(a.fl, fixed, a.depth, grad_z != nullptr, &a.ring_floats)) {
+    set_error("flow kernel shared memory budget exceeded");
+    return LSNF_ERR_INVALID;
+  }
+  const size_t smem = (fixed + a.ring_floats) * 4;
   switch (S) {
     case 1: return launch_fwd_t<1>(a, smem, s);
     case 2: return launch_fwd_t<2>(a, smem, s);
@@ -582,7 +635,12 @@ int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float
   a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
   a.in = eps; a.z_out = z; a.logdet = negobj; a.logp = nullptr; a.grad = nullptr;
   const int S = pick_s(a.B);
-  const size_t smem = flow_smem_floats(a.fl, S, a.depth, false) * 4;
+  const size_t fixed = flow_fixed_floats(a.fl, S, a.depth, false);
+  if (flow_ring_floats(a.fl, fixed, a.depth, false, &a.ring_floats)) {
+    set_error("flow kernel shared memory budget exceeded");
+    return LSNF_ERR_INVALID;
+  }
+  const size_t smem = (fixed + a.ring_floats) * 4;
   switch (S) {
     case 1: return launch_inv_t<1>(a, smem, s);
     case 2: return launch_inv_t<2>(a, smem, s);

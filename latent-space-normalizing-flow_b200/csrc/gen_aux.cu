@@ -99,38 +99,49 @@ int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cud
 // products D[b][iy][ix][tap*nc + c]; each output pixel sums the taps that land on it (fixed order), adds the bias
 // and applies tanh.   x_hat[b][c][oy][ox] = tanh(bias[c] + sum_{ky,kx} D[b][(oy+p-ky)/s][(ox+p-kx)/s][...])
 // ---------------------------------------------------------------------------------------------------
-__global__ void last_gather_tanh_kernel(const float* __restrict__ d, const float* __restrict__ bias,
-                                        float* __restrict__ xhat, int B, int nc, int img, int hin, int k, int s,
-                                        int p, int n_pad) {
+template <int K, int S>
+__global__ void __launch_bounds__(256) last_gather_tanh_kernel(const float* __restrict__ d,
+                                                               const float* __restrict__ bias,
+                                                               float* __restrict__ xhat, int B, int nc, int img,
+                                                               int hin, int p, int n_pad) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * nc * img * img;
   if (i >= total) return;
   const int ox = (int)(i % img), oy = (int)((i / img) % img), c = (int)((i / ((long long)img * img)) % nc);
   const int b = (int)(i / ((long long)img * img * nc));
-  float acc = bias[c];
-  for (int ky = 0; ky < k; ++ky) {
-    const int ty = oy + p - ky;
-    if (ty < 0 || ty % s) continue;
-    const int iy = ty / s;
-    if (iy >= hin) continue;
-    for (int kx = 0; kx < k; ++kx) {
-      const int tx = ox + p - kx;
-      if (tx < 0 || tx % s) continue;
-      const int ix = tx / s;
-      if (ix >= hin) continue;
-      acc += __ldcg(d + (((size_t)b * hin + iy) * hin + ix) * n_pad + (ky * k + kx) * nc + c);
+  // taps along one axis that can land on this pixel: ky = (o + p) % S + S*j, j < K/S (rounded up)
+  constexpr int T = (K + S - 1) / S;
+  float v[T * T];
+  const int ky0 = (oy + p) % S, kx0 = (ox + p) % S;
+#pragma unroll
+  for (int a = 0; a < T; ++a) {
+#pragma unroll
+    for (int e = 0; e < T; ++e) {
+      const int ky = ky0 + S * a, kx = kx0 + S * e;
+      const int iy = (oy + p - ky) / S, ix = (ox + p - kx) / S;   // exact: the numerators are multiples of S
+      const bool ok = ky < K && kx < K && oy + p - ky >= 0 && ox + p - kx >= 0 && iy < hin && ix < hin;
+      v[a * T + e] = ok ? __ldcg(d + (((size_t)b * hin + iy) * hin + ix) * n_pad + (ky * K + kx) * nc + c) : 0.f;
     }
   }
+  float acc = bias[c];
+#pragma unroll
+  for (int t = 0; t < T * T; ++t) acc += v[t];
   xhat[i] = tanhf(acc);
 }
 
 int launch_last_gather(const lsnf_plan* plan, cudaStream_t s) {
   const auto& y = plan->layers[plan->n_layers - 1];
   const long long total = (long long)plan->cfg.batch * plan->cfg.nc * plan->img * plan->img;
-  last_gather_tanh_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      (const float*)(plan->ws + plan->off_dlast), (const float*)(plan->ws + plan->off_bias[plan->n_layers - 1]),
-      (float*)(plan->ws + plan->off_xhat), plan->cfg.batch, plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p,
-      plan->dlast_pad);
+  const float* d = (const float*)(plan->ws + plan->off_dlast);
+  const float* bias = (const float*)(plan->ws + plan->off_bias[plan->n_layers - 1]);
+  float* xh = (float*)(plan->ws + plan->off_xhat);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (y.k == 3 && y.s == 1)
+    last_gather_tanh_kernel<3, 1><<<blocks, 256, 0, s>>>(d, bias, xh, plan->cfg.batch, plan->cfg.nc, plan->img, y.hin,
+                                                        y.p, plan->dlast_pad);
+  else
+    last_gather_tanh_kernel<4, 2><<<blocks, 256, 0, s>>>(d, bias, xh, plan->cfg.batch, plan->cfg.nc, plan->img, y.hin,
+                                                        y.p, plan->dlast_pad);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
