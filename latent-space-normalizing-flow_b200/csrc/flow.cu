@@ -47,49 +47,26 @@ __device__ __forceinline__ void f_bulk_load(uint32_t dst, const float* src, uint
                : "memory");
 }
 
-constexpr int FEED_SLOTS = 8;   // matrices that may be in flight at once (mbarrier slots)
+constexpr int FEED_SLOTS = 8;      // matrices that may be in flight at once (mbarrier slots)
+constexpr int FEED_MAX_ITEMS = 320; // f_depth <= 32, at most 2 passes x 4 matrices per step (+ slack)
 
 // Streams the matrices of the whole pass through a shared-memory byte ring: thread 0 keeps issuing bulk copies for
-// as many upcoming matrices as fit (typically 4-6 in flight, > 100 KB), so the mat-vec chain is bound by one SM's
-// L2 bandwidth instead of by the latency of one copy per step.  Space is reclaimed in FIFO order when the mat-vec
-// that used it has passed its closing __syncthreads.
+// as many upcoming matrices as fit (typically 4-6 in flight, > 100 KB), so the mat-vec chain never waits for a
+// copy.  Space is reclaimed in FIFO order when the mat-vec that used it has passed its closing __syncthreads.
+// The (source offset, size) of every item is tabulated once in shared memory.
 struct Feeder {
   const float* params;
-  FlowLayout f;
-  int depth, perm2, inverse;
   float* ring;            // [ring_floats]
-  float* vbuf[2];         // the per-step vector blocks, double-buffered
+  float* vbase;           // two per-step vector blocks, back to back
+  uint2* items;           // [n_mat] (float offset into params, floats)
   uint32_t* item_off;     // [FEED_SLOTS] placement of each in-flight matrix (floats from `ring`)
   uint32_t* item_fp;      // [FEED_SLOTS] footprint incl. wrap waste
   uint32_t bar0, vbar0;   // shared addresses of the mbarrier arrays
-  uint32_t ring_floats;
+  uint32_t ring_floats, vec_floats, step_floats;
   uint32_t m, v;          // next matrix / vector-block item to be consumed
   uint32_t next_issue, head, used;   // producer state (meaningful in thread 0 only)
-  int n_mat, n_vec, ipl;  // items in the whole launch, matrices per step
+  int n_mat, n_vec, depth, inverse;
 
-  // matrix item -> (offset, floats).  forward pass: per step [W] W1 W2 W3; backward: per step (descending) W3T W2T
-  // W1T [WT]; inverse pass: per step (descending) W1 W2 W3 [Winv]
-  __device__ __forceinline__ void mat_item(int idx, size_t& off, uint32_t& n) const {
-    const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
-    int L, j;
-    bool bwd = false;
-    if (inverse) { L = depth - 1 - idx / ipl; j = idx % ipl; }
-    else if (idx < depth * ipl) { L = idx / ipl; j = idx % ipl + (perm2 ? 0 : 1); }
-    else { bwd = true; idx -= depth * ipl; L = depth - 1 - idx / ipl; j = idx % ipl; }
-    size_t o; uint32_t c;
-    if (inverse) {
-      if (j == 0) { o = f.W1; c = half * w; } else if (j == 1) { o = f.W2; c = w * w; }
-      else if (j == 2) { o = f.W3; c = w * n_out; } else { o = f.Winv; c = nz * nz; }
-    } else if (!bwd) {
-      if (j == 0) { o = f.W; c = nz * nz; } else if (j == 1) { o = f.W1; c = half * w; }
-      else if (j == 2) { o = f.W2; c = w * w; } else { o = f.W3; c = w * n_out; }
-    } else {
-      if (j == 0) { o = f.W3T; c = w * n_out; } else if (j == 1) { o = f.W2T; c = w * w; }
-      else if (j == 2) { o = f.W1T; c = half * w; } else { o = f.WT; c = nz * nz; }
-    }
-    off = (size_t)L * f.step_floats + o;
-    n = c;
-  }
   __device__ __forceinline__ int vec_layer(int idx) const {
     if (inverse) return depth - 1 - idx;
     return idx < depth ? idx : 2 * depth - 1 - idx;
@@ -97,8 +74,8 @@ struct Feeder {
   // thread 0: issue every upcoming matrix that fits into the ring (FIFO allocation with wrap-around)
   __device__ __forceinline__ void pump(uint32_t consumer) {
     while ((int)next_issue < n_mat && next_issue < consumer + FEED_SLOTS - 1) {
-      size_t off; uint32_t n;
-      mat_item((int)next_issue, off, n);
+      const uint2 it = items[next_issue];
+      const uint32_t n = it.y;
       uint32_t place, fp;
       if (used == 0) head = 0;   // empty ring: restart at the beginning (guarantees progress when ring < 2 matrices)
       if (head + n > ring_floats) {
@@ -112,14 +89,14 @@ struct Feeder {
       const uint32_t slot = next_issue % FEED_SLOTS;
       item_off[slot] = place; item_fp[slot] = fp;
       used += fp;
-      f_bulk_load(f_smem_u32(ring + place), params + off, n * 4u, bar0 + 8u * slot);
+      f_bulk_load(f_smem_u32(ring + place), params + it.x, n * 4u, bar0 + 8u * slot);
       ++next_issue;
     }
   }
   __device__ __forceinline__ void issue_vec(int idx) {
     if (idx >= n_vec) return;
-    f_bulk_load(f_smem_u32(vbuf[idx & 1]), params + (size_t)vec_layer(idx) * f.step_floats, (uint32_t)f.vec_floats * 4u,
-                vbar0 + 8u * (idx & 1));
+    f_bulk_load(f_smem_u32(vbase + (idx & 1) * vec_floats), params + (size_t)vec_layer(idx) * step_floats,
+                vec_floats * 4u, vbar0 + 8u * (idx & 1));
   }
   // Returns the staged matrix of the current item.  The previous item's space is reclaimed here: its mat-vec has
   // passed its closing __syncthreads, so no thread reads it any more.
@@ -137,30 +114,55 @@ struct Feeder {
     const uint32_t i = v++;
     f_mbar_wait(vbar0 + 8u * (i & 1), (i >> 1) & 1u);
     if (threadIdx.x == 0) issue_vec((int)i + 1);
-    return vbuf[i & 1];
+    return vbase + (i & 1) * vec_floats;
   }
 };
+
+// matrix item -> (offset, floats).  forward pass: per step [W] W1 W2 W3; backward: per step (descending) W3T W2T
+// W1T [WT]; inverse pass: per step (descending) W1 W2 W3 [Winv]
+__device__ __forceinline__ uint2 flow_mat_item(const FlowLayout& f, int depth, bool perm2, bool inverse, int idx) {
+  const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
+  const int ipl = perm2 ? 4 : 3;
+  int L, j;
+  bool bwd = false;
+  if (inverse) { L = depth - 1 - idx / ipl; j = idx % ipl; }
+  else if (idx < depth * ipl) { L = idx / ipl; j = idx % ipl + (perm2 ? 0 : 1); }
+  else { bwd = true; idx -= depth * ipl; L = depth - 1 - idx / ipl; j = idx % ipl; }
+  size_t o; uint32_t c;
+  if (inverse) {
+    if (j == 0) { o = f.W1; c = half * w; } else if (j == 1) { o = f.W2; c = w * w; }
+    else if (j == 2) { o = f.W3; c = w * n_out; } else { o = f.Winv; c = nz * nz; }
+  } else if (!bwd) {
+    if (j == 0) { o = f.W; c = nz * nz; } else if (j == 1) { o = f.W1; c = half * w; }
+    else if (j == 2) { o = f.W2; c = w * w; } else { o = f.W3; c = w * n_out; }
+  } else {
+    if (j == 0) { o = f.W3T; c = w * n_out; } else if (j == 1) { o = f.W2T; c = w * w; }
+    else if (j == 2) { o = f.W1T; c = half * w; } else { o = f.WT; c = nz * nz; }
+  }
+  return make_uint2((uint32_t)((size_t)L * f.step_floats + o), c);
+}
 
 // carve the dynamic shared memory; returns the first free float
 __device__ __forceinline__ float* feeder_init(Feeder& fd, float* sm, const FlowArgs& a, bool with_bwd, bool inverse) {
   const FlowLayout& f = a.fl;
-  fd.params = a.params; fd.f = f; fd.depth = a.depth; fd.perm2 = a.permutation == 2;
-  fd.inverse = inverse;
-  fd.ipl = fd.perm2 ? 4 : 3;
-  fd.n_mat = a.depth * fd.ipl * ((with_bwd && !inverse) ? 2 : 1);
+  const bool perm2 = a.permutation == 2;
+  const int ipl = perm2 ? 4 : 3;
+  fd.params = a.params; fd.depth = a.depth; fd.inverse = inverse;
+  fd.n_mat = a.depth * ipl * ((with_bwd && !inverse) ? 2 : 1);
   fd.n_vec = a.depth * ((with_bwd && !inverse) ? 2 : 1);
   fd.m = fd.v = 0;
   fd.next_issue = fd.head = fd.used = 0;
-  fd.ring_floats = a.ring_floats;
+  fd.ring_floats = a.ring_floats; fd.vec_floats = (uint32_t)f.vec_floats; fd.step_floats = (uint32_t)f.step_floats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm);   // FEED_SLOTS + 2 mbarriers (the buffer is 16-byte aligned)
   fd.bar0 = f_smem_u32(bars);
   fd.vbar0 = f_smem_u32(bars + FEED_SLOTS);
   fd.item_off = reinterpret_cast<uint32_t*>(bars + FEED_SLOTS + 2);
   fd.item_fp = fd.item_off + FEED_SLOTS;
-  float* p = sm + 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS;
-  fd.vbuf[0] = p; p += f.vec_floats;
-  fd.vbuf[1] = p; p += f.vec_floats;
+  fd.items = reinterpret_cast<uint2*>(fd.item_fp + FEED_SLOTS);
+  float* p = sm + 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS + 2 * FEED_MAX_ITEMS;
+  fd.vbase = p; p += 2 * f.vec_floats;
   fd.ring = p; p += a.ring_floats;
+  for (int i = threadIdx.x; i < fd.n_mat; i += blockDim.x) fd.items[i] = flow_mat_item(f, a.depth, perm2, inverse, i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < FEED_SLOTS + 2; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f_smem_u32(bars + i)));
@@ -171,12 +173,30 @@ __device__ __forceinline__ float* feeder_init(Feeder& fd, float* sm, const FlowA
   return p;
 }
 
-// out[s][j] = epi(s, j, sum_k in[s][k] * M[k*N + j]) for s < S, j < N.  M is row-major [K][N] in SHARED memory
-// (conflict-free along j); `in` lives in shared memory.  The K range is split across 256/Nr thread groups whose
-// partial sums meet in `scratch`.
+// Activations live in shared memory SAMPLE-MINOR: element (sample s, feature j) of a buffer is buf[j*S + s], so a
+// mat-vec reads the S samples of one feature with ONE broadcast vector load.
+template <int S>
+struct SVec { float v[S]; };
+template <int S>
+__device__ __forceinline__ SVec<S> load_samples(const float* p) {
+  SVec<S> r;
+  if constexpr (S == 1) { r.v[0] = p[0]; }
+  else if constexpr (S == 2) { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
+  else {
+#pragma unroll
+    for (int q = 0; q < S; q += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p + q);
+      r.v[q] = t.x; r.v[q + 1] = t.y; r.v[q + 2] = t.z; r.v[q + 3] = t.w;
+    }
+  }
+  return r;
+}
+
+// epi(s, j, sum_k in[k][s] * M[k*N + j]) for s < S, j < N.  M is row-major [K][N] in SHARED memory (conflict-free
+// along j); `in` is a sample-minor [K][S] shared-memory buffer.  The K range is split across 256/Nr thread groups
+// whose partial sums meet in `scratch`.
 template <int S, class Epi>
-__device__ __forceinline__ void matvec(const float* M, int K, int N, const float* in, int ldin, float* scratch,
-                                       Epi epi) {
+__device__ __forceinline__ void matvec(const float* M, int K, int N, const float* in, float* scratch, Epi epi) {
   const int Nr = (N + 31) & ~31;
   const int G = FLOW_THREADS / Nr > 0 ? FLOW_THREADS / Nr : 1;
   const int tid = threadIdx.x;
@@ -189,11 +209,13 @@ __device__ __forceinline__ void matvec(const float* M, int K, int N, const float
       for (int s = 0; s < S; ++s) acc[s] = 0.f;
       const int k0 = g * Kc, k1 = min(K, k0 + Kc);
       const float* m = M + (size_t)k0 * N + j;
+      const float* x = in + (size_t)k0 * S;
 #pragma unroll 8
-      for (int k = k0; k < k1; ++k, m += N) {
+      for (int k = k0; k < k1; ++k, m += N, x += S) {
         const float w = *m;
+        const SVec<S> xv = load_samples<S>(x);
 #pragma unroll
-        for (int s = 0; s < S; ++s) acc[s] = fmaf(in[s * ldin + k], w, acc[s]);
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(xv.v[s], w, acc[s]);
       }
 #pragma unroll
       for (int s = 0; s < S; ++s) scratch[(g * S + s) * Nr + (j - j0)] = acc[s];
@@ -231,6 +253,8 @@ __device__ __forceinline__ void block_sum(float (&v)[S], float* red) {
   __syncthreads();
 }
 
+#define AT(buf, s, j) (buf)[(j) * S + (s)]
+
 template <int S>
 __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) {
   extern __shared__ __align__(16) float sm[];
@@ -238,21 +262,21 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
   const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out;
   const int nmax = max(nz, max(w, n_out));
   const int nr_max = (nmax + 31) & ~31;
-  const int stash_step = 2 * w + nz;  // a1[w], a2[w], scale[half], x2+shift[half]
+  const int stash_step = 2 * w + nz;  // a1[w], a2[w], scale[half], x2+shift[half]  (each x S samples)
   Feeder fd;
-  float* cur = feeder_init(fd, sm, a, a.grad != nullptr, false);   // [S][nz]
-  float* ta = cur + S * nz;                // [S][nmax]
-  float* tb = ta + S * nmax;               // [S][nmax]
+  float* cur = feeder_init(fd, sm, a, a.grad != nullptr, false);   // [nz][S]
+  float* ta = cur + S * nz;                // [nmax][S]
+  float* tb = ta + S * nmax;               // [nmax][S]
   float* scratch = tb + S * nmax;          // partial sums: G*S*Nr <= 256*S
   float* red = scratch + S * max(FLOW_THREADS, nr_max);
-  float* stash = red + (FLOW_THREADS / 32) * S;  // [depth][S][stash_step]
+  float* stash = red + (FLOW_THREADS / 32) * S;  // [depth][stash_step][S]
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * S;
   const int ns = min(S, a.B - b0);
 
   for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-    const int s = i / nz, j = i % nz;
-    cur[i] = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
+    const int s = i / nz, j = i % nz;     // coalesced global read
+    AT(cur, s, j) = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
   }
   __syncthreads();
 
@@ -265,48 +289,46 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
     float* st = stash + (size_t)L * S * stash_step;
     // actnorm (model.py:282-284): (x + b) * exp(3 logs)
     for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-      const int j = i % nz;
-      ta[(i / nz) * nmax + j] = (cur[i] + P[f.an_b + j]) * P[f.an_e + j];
+      const int j = i / S;
+      ta[i] = (cur[i] + P[f.an_b + j]) * P[f.an_e + j];
     }
     __syncthreads();
     if (a.permutation == 2) {   // model.py:187: z @ W
-      matvec<S>(fd.next_mat(), nz, nz, ta, nmax, scratch, [&](int s, int j, float v) { cur[s * nz + j] = v; });
+      matvec<S>(fd.next_mat(), nz, nz, ta, scratch, [&](int s, int j, float v) { AT(cur, s, j) = v; });
     } else {                    // intended shuffle_features: h[:, idx]
       const int* idx = reinterpret_cast<const int*>(P + f.perm);
-      for (int i = tid; i < S * nz; i += FLOW_THREADS) cur[i] = ta[(i / nz) * nmax + idx[i % nz]];
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) cur[i] = AT(ta, i % S, idx[i / S]);
       __syncthreads();
     }
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < S; ++s) ld[s] += P[f.ld_const] , ld[s] += P[f.ld_const + 1];
     }
-    // coupling MLP on x1 = cur[:, :half] (model.py:306-310)
-    float* a1 = st;             // [S][w]
-    float* a2 = st + S * w;     // [S][w]
-    float* sc = a2 + S * w;     // [S][half]
-    float* xs = sc + S * half;  // [S][half]
-    matvec<S>(fd.next_mat(), half, w, cur, nz, scratch,
-              [&](int s, int j, float v) { a1[s * w + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
-    matvec<S>(fd.next_mat(), w, w, a1, w, scratch,
-              [&](int s, int j, float v) { a2[s * w + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
-    matvec<S>(fd.next_mat(), w, n_out, a2, w, scratch,
-              [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    // coupling MLP on x1 = cur[:half] (model.py:306-310)
+    float* a1 = st;             // [w][S]
+    float* a2 = st + S * w;     // [w][S]
+    float* sc = a2 + S * w;     // [half][S]
+    float* xs = sc + S * half;  // [half][S]
+    matvec<S>(fd.next_mat(), half, w, cur, scratch,
+              [&](int s, int j, float v) { AT(a1, s, j) = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
+    matvec<S>(fd.next_mat(), w, w, a1, scratch,
+              [&](int s, int j, float v) { AT(a2, s, j) = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
+    matvec<S>(fd.next_mat(), w, n_out, a2, scratch,
+              [&](int s, int j, float v) { AT(ta, s, j) = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    float* x2 = cur + S * half;   // [half][S]
     if (a.coupling == 1) {      // model.py:410-418
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        const float shift = ta[s * nmax + 2 * j];
-        const float scale = 1.f / (1.f + expf(-(ta[s * nmax + 2 * j + 1] + 2.f)));
-        const float x2s = cur[s * nz + half + j] + shift;
-        cur[s * nz + half + j] = x2s * scale;
+        const int s = i % S, j = i / S;
+        const float shift = AT(ta, s, 2 * j);
+        const float scale = 1.f / (1.f + expf(-(AT(ta, s, 2 * j + 1) + 2.f)));
+        const float x2s = x2[i] + shift;
+        x2[i] = x2s * scale;
         sc[i] = scale; xs[i] = x2s;
 #pragma unroll
         for (int q = 0; q < S; ++q) if (q == s) ld[q] += logf(scale);
       }
     } else {                    // model.py:407-408
-      for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        cur[s * nz + half + j] += ta[s * nmax + j];
-      }
+      for (int i = tid; i < S * half; i += FLOW_THREADS) x2[i] += ta[i];
     }
     __syncthreads();
   }
@@ -317,7 +339,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
 #pragma unroll
   for (int s = 0; s < S; ++s) sq[s] = 0.f;
   for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-    const int s = i / nz;
+    const int s = i % S;
     const float v = cur[i];
 #pragma unroll
     for (int q = 0; q < S; ++q) if (q == s) sq[q] += -0.5f * v * v;
@@ -334,13 +356,14 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
   }
   if (a.z_out)
     for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-      const int s = i / nz;
-      if (s < ns) a.z_out[(size_t)(b0 + s) * nz + i % nz] = cur[i];
+      const int s = i / nz, j = i % nz;
+      if (s < ns) a.z_out[(size_t)(b0 + s) * nz + j] = AT(cur, s, j);
     }
   if (!a.grad) return;
 
   // ---- analytic backward of -sum_b ll_b: seed g = z_out, d/dlogdet = -1 ----
-  float* g = cur;  // in place
+  float* g = cur;  // in place, [nz][S]
+  float* g2p = g + S * half;
   for (int L = a.depth - 1; L >= 0; --L) {
     const float* P = fd.next_vec();
     float* st = stash + (size_t)L * S * stash_step;
@@ -351,45 +374,39 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
     // gradient w.r.t. the MLP output h, already multiplied by e3 = exp(3 logs_zeros)
     if (a.coupling == 1) {
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        const float g2 = g[s * nz + half + j], scale = sc[i];
+        const int s = i % S, j = i / S;
+        const float g2 = g2p[i], scale = sc[i];
         const float g_shift = g2 * scale;
         const float g_scale = g2 * xs[i] - 1.f / scale;
-        ta[s * nmax + 2 * j] = g_shift * P[f.e3 + 2 * j];
-        ta[s * nmax + 2 * j + 1] = g_scale * scale * (1.f - scale) * P[f.e3 + 2 * j + 1];
-        g[s * nz + half + j] = g_shift;  // = g_x2
+        AT(ta, s, 2 * j) = g_shift * P[f.e3 + 2 * j];
+        AT(ta, s, 2 * j + 1) = g_scale * scale * (1.f - scale) * P[f.e3 + 2 * j + 1];
+        g2p[i] = g_shift;  // = g_x2
       }
     } else {
-      for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        ta[s * nmax + j] = g[s * nz + half + j] * P[f.e3 + j];
-      }
+      for (int i = tid; i < S * half; i += FLOW_THREADS) ta[i] = g2p[i] * P[f.e3 + i / S];
     }
     __syncthreads();
-    matvec<S>(fd.next_mat(), n_out, w, ta, nmax, scratch,
-              [&](int s, int j, float v) { tb[s * nmax + j] = a2[s * w + j] > 0.f ? v * P[f.e2 + j] : 0.f; });
-    matvec<S>(fd.next_mat(), w, w, tb, nmax, scratch,
-              [&](int s, int j, float v) { ta[s * nmax + j] = a1[s * w + j] > 0.f ? v * P[f.e1 + j] : 0.f; });
-    matvec<S>(fd.next_mat(), w, half, ta, nmax, scratch, [&](int s, int j, float v) { g[s * nz + j] += v; });
+    matvec<S>(fd.next_mat(), n_out, w, ta, scratch,
+              [&](int s, int j, float v) { AT(tb, s, j) = AT(a2, s, j) > 0.f ? v * P[f.e2 + j] : 0.f; });
+    matvec<S>(fd.next_mat(), w, w, tb, scratch,
+              [&](int s, int j, float v) { AT(ta, s, j) = AT(a1, s, j) > 0.f ? v * P[f.e1 + j] : 0.f; });
+    matvec<S>(fd.next_mat(), w, half, ta, scratch, [&](int s, int j, float v) { AT(g, s, j) += v; });
+    for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[i] = g[i];
+    __syncthreads();
     if (a.permutation == 2) {   // g @ W^T, then the actnorm scale
-      for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[(i / nz) * nmax + i % nz] = g[i];
-      __syncthreads();
-      matvec<S>(fd.next_mat(), nz, nz, ta, nmax, scratch,
-                [&](int s, int j, float v) { g[s * nz + j] = v * P[f.an_e + j]; });
+      matvec<S>(fd.next_mat(), nz, nz, ta, scratch, [&](int s, int j, float v) { AT(g, s, j) = v * P[f.an_e + j]; });
     } else {
       const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
-      for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[(i / nz) * nmax + i % nz] = g[i];
-      __syncthreads();
       for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-        const int j = i % nz;
-        g[i] = ta[(i / nz) * nmax + inv[j]] * P[f.an_e + j];
+        const int s = i % S, j = i / S;
+        g[i] = AT(ta, s, inv[j]) * P[f.an_e + j];
       }
       __syncthreads();
     }
   }
   for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-    const int s = i / nz;
-    if (s < ns) a.grad[(size_t)(b0 + s) * nz + i % nz] = g[i];
+    const int s = i / nz, j = i % nz;
+    if (s < ns) a.grad[(size_t)(b0 + s) * nz + j] = AT(g, s, j);
   }
 }
 
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
   const int nmax = max(nz, max(w, n_out));
   const int nr_max = (nmax + 31) & ~31;
   Feeder fd;
-  float* cur = feeder_init(fd, sm, a, false, true);
+  float* cur = feeder_init(fd, sm, a, false, true);   // [nz][S]
   float* ta = cur + S * nz;
   float* tb = ta + S * nmax;
   float* scratch = tb + S * nmax;
@@ -412,46 +429,44 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
   const int ns = min(S, a.B - b0);
   for (int i = tid; i < S * nz; i += FLOW_THREADS) {
     const int s = i / nz, j = i % nz;
-    cur[i] = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
+    AT(cur, s, j) = s < ns ? a.in[(size_t)(b0 + s) * nz + j] : 0.f;
   }
   __syncthreads();
   float ld[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) ld[s] = 0.f;
+  float* x2 = cur + S * half;
   for (int L = a.depth - 1; L >= 0; --L) {
     const float* P = fd.next_vec();
-    matvec<S>(fd.next_mat(), half, w, cur, nz, scratch,
-              [&](int s, int j, float v) { ta[s * nmax + j] = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
-    matvec<S>(fd.next_mat(), w, w, ta, nmax, scratch,
-              [&](int s, int j, float v) { tb[s * nmax + j] = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
-    matvec<S>(fd.next_mat(), w, n_out, tb, nmax, scratch,
-              [&](int s, int j, float v) { ta[s * nmax + j] = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    matvec<S>(fd.next_mat(), half, w, cur, scratch,
+              [&](int s, int j, float v) { AT(ta, s, j) = fmaxf((v + P[f.b1 + j]) * P[f.e1 + j], 0.f); });
+    matvec<S>(fd.next_mat(), w, w, ta, scratch,
+              [&](int s, int j, float v) { AT(tb, s, j) = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
+    matvec<S>(fd.next_mat(), w, n_out, tb, scratch,
+              [&](int s, int j, float v) { AT(ta, s, j) = (v + P[f.b3 + j]) * P[f.e3 + j]; });
     if (a.coupling == 1) {      // model.py:432-438
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        const float shift = ta[s * nmax + 2 * j];
-        const float scale = 1.f / (1.f + expf(-(ta[s * nmax + 2 * j + 1] + 2.f)));
-        cur[s * nz + half + j] = cur[s * nz + half + j] / scale - shift;
+        const int s = i % S, j = i / S;
+        const float shift = AT(ta, s, 2 * j);
+        const float scale = 1.f / (1.f + expf(-(AT(ta, s, 2 * j + 1) + 2.f)));
+        x2[i] = x2[i] / scale - shift;
 #pragma unroll
         for (int q = 0; q < S; ++q) if (q == s) ld[q] -= logf(scale);
       }
     } else {                    // model.py:429-430
-      for (int i = tid; i < S * half; i += FLOW_THREADS) {
-        const int s = i / half, j = i % half;
-        cur[s * nz + half + j] -= ta[s * nmax + j];
-      }
+      for (int i = tid; i < S * half; i += FLOW_THREADS) x2[i] -= ta[i];
     }
     __syncthreads();
-    for (int i = tid; i < S * nz; i += FLOW_THREADS) tb[(i / nz) * nmax + i % nz] = cur[i];
+    for (int i = tid; i < S * nz; i += FLOW_THREADS) tb[i] = cur[i];
     __syncthreads();
     if (a.permutation == 2) {   // model.py:193-196: z @ inverse(W), then actnorm reverse (:288-291)
-      matvec<S>(fd.next_mat(), nz, nz, tb, nmax, scratch,
-                [&](int s, int j, float v) { cur[s * nz + j] = v * P[f.an_ei + j] - P[f.an_b + j]; });
+      matvec<S>(fd.next_mat(), nz, nz, tb, scratch,
+                [&](int s, int j, float v) { AT(cur, s, j) = v * P[f.an_ei + j] - P[f.an_b + j]; });
     } else {
       const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
       for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-        const int j = i % nz;
-        cur[i] = tb[(i / nz) * nmax + inv[j]] * P[f.an_ei + j] - P[f.an_b + j];
+        const int s = i % S, j = i / S;
+        cur[i] = AT(tb, s, inv[j]) * P[f.an_ei + j] - P[f.an_b + j];
       }
       __syncthreads();
     }
@@ -468,10 +483,11 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_inverse_kernel(FlowArgs a) 
       if (s < ns) a.logdet[b0 + s] = -ld[s];   // the reference returns -objective (model.py:498)
   }
   for (int i = tid; i < S * nz; i += FLOW_THREADS) {
-    const int s = i / nz;
-    if (s < ns) a.z_out[(size_t)(b0 + s) * nz + i % nz] = cur[i];
+    const int s = i / nz, j = i % nz;
+    if (s < ns) a.z_out[(size_t)(b0 + s) * nz + j] = AT(cur, s, j);
   }
 }
+#undef AT
 
 // ---------------------------------------------------------------------------------------------------
 // parameter packing: one launch per flow step; builds transposes, exp(+-3 logs) and the log-det constants
@@ -564,7 +580,7 @@ static int pick_s(int B) {
 static size_t flow_fixed_floats(const FlowLayout& f, int S, int depth, bool stash) {
   const int nmax = std::max(f.nz, std::max(f.w, f.n_out));
   const int nr_max = (nmax + 31) & ~31;
-  size_t n = 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS + 2 * f.vec_floats +   // mbarriers, ring bookkeeping, vector blocks
+  size_t n = 2 * (FEED_SLOTS + 2) + 2 * FEED_SLOTS + 2 * FEED_MAX_ITEMS + 2 * f.vec_floats +   // mbarriers, ring bookkeeping, item table, vector blocks
              (size_t)S * f.nz + 2 * (size_t)S * nmax + (size_t)S * std::max(FLOW_THREADS, nr_max) +
              (size_t)(FLOW_THREADS / 32) * S;
   if (stash) n += (size_t)depth * S * (2 * f.w + f.nz);

@@ -632,12 +632,18 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
   for (int t = 0; t < steps; ++t) {
     tr.on = trace_env == 1 && t == 1 && !dyn;
     tr.mark("start");
-    // fork: the flow prior (train.py:316-323) only needs z; it overlaps the generator stages on the side stream
-    LSNF_CUDA(cudaEventRecord(plan->ev_fork, s));
-    LSNF_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-    if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, plan->side))) return rc;
-    LSNF_CUDA(cudaEventRecord(plan->ev_join, plan->side));
+    // The flow prior (train.py:316-323) only needs z and runs on the side stream.  It is forked right before the
+    // last forward layer so that it overlaps the short, non-persistent kernels (last layer, gather, loss-gradient
+    // seed): its few CTAs hold whole SMs for tens of microseconds, which would otherwise delay the cluster launch
+    // of the persistent CTA-pair GEMMs.
+    const int fork_at = plan->n_layers - 1;
     for (int l = 0; l < plan->n_layers; ++l) {
+      if (l == fork_at) {
+        LSNF_CUDA(cudaEventRecord(plan->ev_fork, s));
+        LSNF_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, plan->side))) return rc;
+        LSNF_CUDA(cudaEventRecord(plan->ev_join, plan->side));
+      }
       if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
       tr.mark(("forward layer " + std::to_string(l)).c_str());
     }
