@@ -57,13 +57,18 @@ struct StageDev {
   int32_t fp16, out_fp16;             // operand / hi|lo-output element format: 1 = fp16, 0 = bf16
   const float* descale;               // accumulators are multiplied by *descale (weights packed times 2^k), or null
   int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
+  float* sk_slots;                    // stream-K: one fp32 partial accumulator [128][256] per CTA of the pair grid
+  int32_t* sk_flags;                  // stream-K: one flag per (CTA, epilogue warp), 0 = empty, 1 = partial ready
+  int32_t sk_enable, pad2_;           // stream-K on/off for this launch
+  int32_t out_tma, pad3_;             // hi|lo output written by TMA tensor stores: 1 up2 forward, 2 first layer,
+                                      // 3 plain gradient, 4 phase-split gradient; 0 = per-thread stores           // 1: equal shares of (tiles x K blocks) per CTA pair; 0: whole tiles, strided
   PhaseDev ph[LSNF_MAX_PHASES];
 };
 
 struct StageHost {
   lsnf_stage_info info;
   StageDev dev;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   bool maps_ready = false;
   int layer = 0;
   int kind = 0;      // 0 fwd, 1 bwd
@@ -114,7 +119,7 @@ struct lsnf_plan {
   struct LoopGraph { int steps; float step_size, sigma; int with_noise; cudaGraphExec_t exec; };
   std::vector<LoopGraph> graphs;
   cudaStream_t cap_stream = nullptr;
-  size_t off_x = 0, off_gnorms = 0, off_dyn = 0;
+  size_t off_x = 0, off_gnorms = 0, off_dyn = 0, off_sk_slots = 0, off_sk_flags = 0;
   long long runs = 0;
   bool use_graphs = true;
 };

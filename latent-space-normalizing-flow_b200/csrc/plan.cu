@@ -203,6 +203,8 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
 
   if (L > 0) {
     p->off_zhl = take((size_t)B * 2 * p->kp * 2);
+    p->off_sk_slots = take((size_t)160 * 128 * 256 * 4);   // stream-K partial accumulators (<= 160 CTAs)
+    p->off_sk_flags = take((size_t)160 * 8 * 4);
     p->off_x = take((size_t)B * c.nc * p->img * p->img * 4);
     for (int l = 0; l < L - 1; ++l) {
       const auto& y = p->layers[l];
@@ -439,6 +441,8 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
     d.b = (const __nv_bfloat16*)(plan->ws + st.b_off);
     d.out = plan->ws + st.out_off;
     d.bias = (st.kind == 0 && !st.last) ? (const float*)(plan->ws + st.bias_off) : nullptr;
+    d.sk_slots = (float*)(plan->ws + plan->off_sk_slots);
+    d.sk_flags = (int32_t*)(plan->ws + plan->off_sk_flags);
     d.descale = st.kind == 0 ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 8) : nullptr;
     d.mask = (st.kind == 1 && !st.first) ? (const __nv_bfloat16*)(plan->ws + st.mask_off) : nullptr;
     if (plan->cfg.gemm_impl == LSNF_GEMM_TCGEN05) {

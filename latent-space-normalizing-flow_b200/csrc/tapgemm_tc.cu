@@ -21,6 +21,9 @@ namespace lsnf {
 constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half the columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB per hi or lo half
+// L2 eviction-priority hints (the encodings createpolicy.fractional.L2::evict_{first,last} produce for fraction 1.0)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
 template <int BN>
 struct TcCfg {
@@ -122,10 +125,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // split the columns.  Row-invariant addressing is hoisted out of the column loop, and the saved-activation signs a
 // data-gradient row needs are fetched BEFORE waiting for the accumulator, i.e. while the main loop still runs.
 // Reference semantics: bias + LeakyReLU of model.py:56-151; LeakyReLU' for the data gradient (train.py:314).
+// Stream-K (CTA-pair kernel): `sk_mode` 1 = this CTA computed only the head of the tile's K range: the raw fp32
+// accumulator goes to this CTA's slot and the warp's flag is raised; 2 = this CTA computed the tail: the partials
+// of the CTAs [sk_first, sk_self) are added before the normal epilogue.  Flags are per (CTA, epilogue warp) -- the
+// warps of the two CTAs own the same rows and columns -- and are reset by their single consumer, so they are 0
+// again at the next launch (CUDA-graph replays included).
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n0, int phase, int split, int warp,
                                             int lane, uint32_t tmem_acc, uint32_t full_bar, uint32_t parity,
-                                            bool have_acc) {
+                                            bool have_acc, int sk_mode = 0, int sk_self = 0, int sk_first = 0,
+                                            int sk_stride = 2) {
   using Cfg = TcCfg<BN>;
   const int quarter = warp & 3;
   const int half = (warp - 2) >> 2;
@@ -172,12 +181,56 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
   if (have_acc) mbar_wait(full_bar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!active) return;
+  const int ewarp = warp - 2;
+  if (sk_mode == 1) {
+    // helper: raw accumulator -> slot[sk_self], stored COLUMN-major ([256 columns][128 rows]) so that the 32 lanes
+    // of a warp (32 consecutive rows) write 128 contiguous bytes per column; then raise this warp's flag
+    float* slot = st.sk_slots + ((size_t)sk_self * 256 + c_begin) * BLOCK_M + r;
+#pragma unroll
+    for (int cc = 0; cc < SPAN; cc += CH) {
+      uint32_t v[CH];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c_begin + cc);
+      if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < CH; ++j) slot[(size_t)(cc + j) * BLOCK_M] = __uint_as_float(v[j]);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      volatile int32_t* flag = st.sk_flags + sk_self * TC_EPI_WARPS + ewarp;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+    }
+    return;
+  }
+  if (sk_mode == 2) {
+    // finisher: wait until every helper CTA of this tile has published this warp's part
+    if (lane == 0) {
+      for (int h = sk_first; h < sk_self; h += sk_stride) {
+        const int32_t* flag = st.sk_flags + h * TC_EPI_WARPS + ewarp;
+        int32_t f;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+        } while (f == 0);
+      }
+    }
+    __syncwarp();
+    __threadfence();
+  }
 #pragma unroll
   for (int cc = 0; cc < SPAN; cc += CH) {
     uint32_t v[CH];
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c_begin + cc);
     if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (sk_mode == 2) {
+      for (int h = sk_first; h < sk_self; h += sk_stride) {
+        const float* slot = st.sk_slots + ((size_t)h * 256 + c_begin + cc) * BLOCK_M + r;
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(slot + (size_t)j * BLOCK_M));
+      }
+    }
     if (!ok) continue;
 #pragma unroll
     for (int j = 0; j < CH; j += 8) {
@@ -212,6 +265,11 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
         *reinterpret_cast<float4*>(o32 + cc + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
       }
     }
+  }
+  if (sk_mode == 2) {
+    __syncwarp();
+    if (lane == 0)
+      for (int h = sk_first; h < sk_self; h += sk_stride) st.sk_flags[h * TC_EPI_WARPS + ewarp] = 0;
   }
 }
 
@@ -326,20 +384,21 @@ constexpr int P_BN = 256;
 constexpr int P_B_TILE_BYTES = (P_BN / 2) * BLOCK_K * 2;                 // this CTA's half of the weight rows
 constexpr int P_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * P_B_TILE_BYTES;      // 64 KiB per CTA
 constexpr int P_STAGES = 3;
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;   // 3 x 64 KiB ring + alignment + barriers
+constexpr int P_EPI_STAGING = 2 * BLOCK_M * 128;                           // hi + lo slab of 128 rows x 64 channels
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_EPI_STAGING + 1024 + 256;   // ring + staging + align + barriers
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;                            // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                              int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(L2_EVICT_LAST)
       : "memory");
 }
 __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(L2_EVICT_LAST)
       : "memory");
 }
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -371,23 +430,228 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 
-// Persistent: one CTA pair per SM pair walks the tile list (m-pair fastest, so consecutive tiles share weights in
-// L2).  The shared-memory ring keeps streaming across tile boundaries, and the 512 TMEM columns hold TWO 256-column
-// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// Outputs are written once and not re-read by this kernel: evict-first keeps them from displacing the operands,
+// which every tap re-reads from L2.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(map),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(L2_EVICT_FIRST)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {   // the 8 epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+}
+
+// Epilogue of the CTA-pair kernel for the hi|lo outputs, through shared memory and TMA tensor stores.
+// Per-thread 16-byte stores of a thread-per-row layout touch 32 different 1 KB-strided rows per instruction; they
+// cost the wide stages ~20 % and made the last layer's data gradient store-bound.  Here the 8 warps cooperate on one
+// 64-channel slab at a time: warp (quarter, half) converts rows [32*quarter, +32) x channels [32*half, +32) into the
+// 128-byte-swizzled staging tile (hi and lo, 16 KiB each), then one thread issues two 5-D tensor stores (the box
+// scatters rows to their strided / phase-split positions and clips the ragged batch).
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtensorMap* tmO, uint32_t stage_smem,
+                                                int mtile, int n0, int phase, int warp, int lane, uint32_t tmem_acc,
+                                                uint32_t full_bar, uint32_t parity, int sk_mode, int sk_self,
+                                                int sk_first) {
+  const int quarter = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int ewarp = warp - 2;
+  const int r = quarter * 32 + lane;
+  const RowCtx rc = tile_row(st, mtile, r);
+  const int epi = st.epi;
+  const float leak = st.leak;
+  const bool out16 = st.out_fp16 != 0;
+  constexpr int NCH = BN / 64;   // 64-channel slabs per tile
+  // saved-activation signs for this thread's 32 channels of every slab (prefetched while the main loop runs)
+  uint4 mk[NCH * 4];
+  if (epi == EPI_GRAD_HL && rc.valid) {
+    const uint16_t* mrow = (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + n0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mk[ch * 4 + j] = __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64 + half * 32) + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NCH * 4; ++j) mk[j] = make_uint4(0, 0, 0, 0);
+  }
+  // tensor-store coordinates of this tile
+  int b0, h0, w0;
+  tile_origin(st, mtile, b0, h0, w0);
+  const int cb = n0 % st.oC;
+  int c1, c2, c3, c4;
+  if (st.out_tma == 1) { c1 = st.ph[phase].no; c2 = w0; c3 = st.ph[phase].mo; c4 = b0 * st.Hg + h0; }
+  else if (st.out_tma == 2) { c1 = n0 / st.oC; c2 = 0; c3 = 0; c4 = b0; }
+  else if (st.out_tma == 3) { c1 = w0; c2 = h0; c3 = b0; c4 = 0; }
+  else { c1 = w0 >> 1; c2 = b0 * (st.Hg >> 1) + (h0 >> 1); c3 = 0; c4 = 0; }
+  // staging row of this thread's tile row: identity, except for the phase-split gradient whose box is ordered
+  // (py, px, b*H/2 + m/2, n/2) so that the tensor map's strides increase monotonically
+  int srow = r;
+  if (st.out_tma == 4) {
+    const int nl = r % st.bW, ml = (r / st.bW) % st.bH, bl = r / (st.bW * st.bH);
+    srow = (((ml & 1) * 2 + (nl & 1)) * (st.bB * (st.bH >> 1)) + bl * (st.bH >> 1) + (ml >> 1)) * (st.bW >> 1) + (nl >> 1);
+  }
+  const float* bias = (epi == EPI_ACT_HL) ? st.bias + cb + half * 32 : nullptr;
+  const float descale = st.descale ? __ldg(st.descale) : 1.f;
+  const uint32_t hi_buf = stage_smem, lo_buf = stage_smem + 128 * 128;
+
+  mbar_wait(full_bar, parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (sk_mode == 2) {
+    if (lane == 0) {
+      for (int h = sk_first; h < sk_self; h += 2) {
+        const int32_t* flag = st.sk_flags + h * TC_EPI_WARPS + ewarp;
+        int32_t f;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+        } while (f == 0);
+      }
+    }
+    __syncwarp();
+    __threadfence();
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int col = ch * 64 + half * 32;   // column of the accumulator tile
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (sk_mode == 2) {
+      for (int h = sk_first; h < sk_self; h += 2) {
+        // column-major slot: coalesced across the warp's 32 rows
+        const float* slot = st.sk_slots + ((size_t)h * 256 + col) * BLOCK_M + r;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(slot + (size_t)j * BLOCK_M));
+      }
+    }
+    // the previous slab's tensor stores have finished reading the staging tile (the issuing thread waited for
+    // that before arriving here)
+    epi_bar_sync();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __align__(16) uint16_t hi[8], lo[8];
+      if (epi == EPI_ACT_HL) {
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(bias + ch * 64 + j));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(bias + ch * 64 + j + 4));
+        const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float t = __uint_as_float(v[j + q]) * descale + bb[q];
+          t = t > 0.f ? t : t * leak;
+          split16(t, out16, hi[q], lo[q]);
+        }
+      } else {
+        const uint16_t* mv = reinterpret_cast<const uint16_t*>(&mk[ch * 4 + j / 8]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a = __uint_as_float(v[j + q]) * descale;
+          split16((mv[q] & 0x8000u) ? a * leak : a, out16, hi[q], lo[q]);
+        }
+      }
+      // row r of the slab is 128 B; the 16-byte chunk index is XORed with (row % 8) -- the 128-byte TMA swizzle
+      const uint32_t chunk = (uint32_t)(half * 4 + j / 8) ^ (uint32_t)(srow & 7);
+      const uint32_t off = (uint32_t)srow * 128u + chunk * 16u;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_buf + off), "r"(((uint32_t*)hi)[0]),
+                   "r"(((uint32_t*)hi)[1]), "r"(((uint32_t*)hi)[2]), "r"(((uint32_t*)hi)[3])
+                   : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_buf + off), "r"(((uint32_t*)lo)[0]),
+                   "r"(((uint32_t*)lo)[1]), "r"(((uint32_t*)lo)[2]), "r"(((uint32_t*)lo)[3])
+                   : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar_sync();
+    if (warp == 2 && lane == 0) {
+      const int c0 = cb + ch * 64;
+      tma_store_5d(tmO, hi_buf, c0, c1, c2, c3, c4);
+      tma_store_5d(tmO, lo_buf, c0 + st.oC, c1, c2, c3, c4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  }
+  if (sk_mode == 2) {
+    __syncwarp();
+    if (lane == 0)
+      for (int h = sk_first; h < sk_self; h += 2) st.sk_flags[h * TC_EPI_WARPS + ewarp] = 0;
+  }
+}
+
+// Work list of one CTA pair under stream-K.  The stage's tiles (m-pair fastest, so consecutive tiles share weights
+// in L2) times their K blocks form one linear range of units, cut into equal contiguous shares; a share that ends
+// inside a tile makes its owner a HELPER for that tile (it publishes a raw partial accumulator), one that starts
+// inside a tile a FINISHER (it adds the helpers' partials, then runs the normal epilogue).  The helper item is
+// processed FIRST and the finisher item LAST, so nobody ever waits long for a partial.
+struct SkItem { int tile, ka, kb, mode; };   // mode 0 full, 1 helper, 2 finisher
+struct SkPlan {
+  int total, t_lo, t_hi, ka_lo, kb_hi, first_fin, last_help, first_help_only, n_items, full_lo, full_hi;
+  long long u0, u1;
+  int strided, pair_, npairs_;
+  __device__ __forceinline__ void init(int pair, int num_pairs, int num_tiles, int total_, bool stream_k) {
+    total = total_;
+    strided = !stream_k; pair_ = pair; npairs_ = num_pairs;
+    if (strided) {   // whole tiles: pair, pair + P, pair + 2P, ...
+      n_items = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+      first_fin = last_help = first_help_only = 0;
+      return;
+    }
+    const long long U = (long long)num_tiles * total;
+    u0 = U * pair / num_pairs; u1 = U * (pair + 1) / num_pairs;
+    n_items = 0; first_fin = last_help = first_help_only = 0; full_lo = 0; full_hi = -1;
+    if (u1 <= u0) return;
+    t_lo = (int)(u0 / total); t_hi = (int)((u1 - 1) / total);
+    ka_lo = (int)(u0 - (long long)t_lo * total);
+    kb_hi = (int)(u1 - (long long)t_hi * total);          // in (0, total]
+    const bool first_cut = ka_lo != 0, last_cut = kb_hi != total;
+    if (t_lo == t_hi) {
+      if (last_cut) { last_help = 1; }                     // a share inside one tile that does not reach its end
+      else if (first_cut) { first_fin = 1; }
+      else { full_lo = full_hi = t_lo; }
+    } else {
+      last_help = last_cut; first_fin = first_cut;
+      full_lo = first_cut ? t_lo + 1 : t_lo;
+      full_hi = last_cut ? t_hi - 1 : t_hi;
+    }
+    n_items = last_help + (full_hi >= full_lo ? full_hi - full_lo + 1 : 0) + first_fin;
+  }
+  __device__ __forceinline__ SkItem item(int j) const {
+    SkItem it;
+    if (strided) { it.tile = pair_ + j * npairs_; it.ka = 0; it.kb = total; it.mode = 0; return it; }
+    if (last_help) {
+      if (j == 0) { it.tile = t_hi; it.ka = (t_lo == t_hi) ? ka_lo : 0; it.kb = kb_hi; it.mode = 1; return it; }
+      --j;
+    }
+    const int nfull = full_hi >= full_lo ? full_hi - full_lo + 1 : 0;
+    if (j < nfull) { it.tile = full_lo + j; it.ka = 0; it.kb = total; it.mode = 0; return it; }
+    it.tile = t_lo; it.ka = ka_lo; it.kb = total; it.mode = 2;
+    return it;
+  }
+};
+
+// first pair whose share contains unit u (shares are [U*p/P, U*(p+1)/P))
+__device__ __forceinline__ int sk_pair_of(long long u, long long U, int P) {
+  int p = (int)((u * P) / U);
+  while (p > 0 && U * p / P > u) --p;
+  while (p + 1 < P && U * (p + 1) / P <= u) ++p;
+  return p;
+}
+
+// Persistent: one CTA pair per SM pair.  The shared-memory ring keeps streaming across tile boundaries, and the 512
+// TMEM columns hold TWO 256-column accumulators so the epilogue of item i overlaps the main loop of item i+1.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ StageDev st) {
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ StageDev st) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = tiles + P_STAGES * P_STAGE_BYTES;
+  const uint32_t stage_smem = tiles + P_STAGES * P_STAGE_BYTES;   // 32 KiB epilogue staging (hi, lo slabs)
+  const uint32_t bars = stage_smem + P_EPI_STAGING;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (P_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * P_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * P_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * P_STAGES + 4);
   uint8_t* gen_base = smem_raw + (tiles - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(gen_base + P_STAGES * P_STAGE_BYTES + 8 * (2 * P_STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      gen_base + P_STAGES * P_STAGE_BYTES + P_EPI_STAGING + 8 * (2 * P_STAGES + 4));
 
   uint32_t cta_rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -399,16 +663,20 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int m_pairs = (mtiles + 1) >> 1, n_tiles = st.n_pad / P_BN;
   const int num_tiles = m_pairs * n_tiles * st.nphase;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int total = st.ph[0].ntaps * kblocks;   // identical for every phase of a stage (checked on the host)
+  SkPlan sk;
+  sk.init(pair_id, num_pairs, num_tiles, total, st.sk_enable != 0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (st.out_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
     for (int s = 0; s < P_STAGES; ++s) {
       mbar_init(full_bar(s), 1);    // leader's producer arrives once per use (+ the bytes of both CTAs)
       mbar_init(empty_bar(s), 1);   // one multicast commit per use
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1);                     // multicast commit of the tile's last MMA
+      mbar_init(tmem_full_bar(a), 1);                     // multicast commit of the item's last MMA
       mbar_init(tmem_empty_bar(a), 2 * TC_EPI_WARPS);     // every epilogue warp of both CTAs (leader's copy is used)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -427,15 +695,16 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer (both CTAs); completions of both land on the LEADER's full barrier =====
-      uint32_t i = 0;   // running K-block counter: the ring does not drain between tiles
-      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      uint32_t i = 0;   // running K-block counter: the ring does not drain between items
+      for (int j = 0; j < sk.n_items; ++j) {
+        const SkItem w = sk.item(j);
+        const int t = w.tile;
         const int mp = t % m_pairs, nt = (t / m_pairs) % n_tiles, phase = t / (m_pairs * n_tiles);
         const int mtile = 2 * mp + (int)cta_rank;
         int b0, h0, w0;
         tile_origin(st, mtile, b0, h0, w0);
         const int nb = nt * P_BN + (int)cta_rank * (P_BN / 2);
-        const int total = st.ph[phase].ntaps * kblocks;
-        for (int it = 0; it < total; ++it, ++i) {
+        for (int it = w.ka; it < w.kb; ++it, ++i) {
           const int s = i % P_STAGES;
           const uint32_t par = (i / P_STAGES) & 1u;
           mbar_wait(empty_bar(s), par ^ 1u);
@@ -458,16 +727,15 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ===== MMA issuer (leader CTA only): M = 256 over both CTAs, N = 256 =====
       const uint32_t fmt = st.fp16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      uint32_t i = 0, lt = 0;
-      for (int t = pair_id; t < num_tiles; t += num_pairs, ++lt) {
-        const int phase = t / (m_pairs * n_tiles);
-        const int total = st.ph[phase].ntaps * kblocks;
-        const uint32_t acc = lt & 1u;
-        // the epilogues of both CTAs must have drained this accumulator (two tiles ago)
-        mbar_wait(tmem_empty_bar(acc), ((lt >> 1) & 1u) ^ 1u);
+      uint32_t i = 0;
+      for (int j = 0; j < sk.n_items; ++j) {
+        const SkItem w = sk.item(j);
+        const uint32_t acc = (uint32_t)j & 1u;
+        // the epilogues of both CTAs must have drained this accumulator (two items ago)
+        mbar_wait(tmem_empty_bar(acc), (((uint32_t)j >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * P_BN;
-        for (int it = 0; it < total; ++it, ++i) {
+        for (int it = w.ka; it < w.kb; ++it, ++i) {
           const int s = i % P_STAGES;
           const uint32_t par = (i / P_STAGES) & 1u;
           mbar_wait(full_bar(s), par);
@@ -478,7 +746,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + P_B_TILE_BYTES + k * 32);
-            umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
             umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
             umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
           }
@@ -488,14 +756,23 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue warps: tile lt reads accumulator lt & 1, then hands it back to the MMA issuer =====
-    uint32_t lt = 0;
-    for (int t = pair_id; t < num_tiles; t += num_pairs, ++lt) {
+    // ===== epilogue warps: item j reads accumulator j & 1, then hands it back to the MMA issuer =====
+    const long long U = (long long)num_tiles * total;
+    for (int j = 0; j < sk.n_items; ++j) {
+      const SkItem w = sk.item(j);
+      const int t = w.tile;
       const int mp = t % m_pairs, nt = (t / m_pairs) % n_tiles, phase = t / (m_pairs * n_tiles);
       const int mtile = 2 * mp + (int)cta_rank;
-      const uint32_t acc = lt & 1u;
-      tc_epilogue<P_BN>(st, mtile, nt * P_BN, phase, 0, warp, lane, tmem_base + acc * P_BN, tmem_full_bar(acc),
-                        (lt >> 1) & 1u, true);
+      const uint32_t acc = (uint32_t)j & 1u;
+      const int self = 2 * pair_id + (int)cta_rank;       // slot / flag index of this CTA
+      int first = self;
+      if (w.mode == 2) first = 2 * sk_pair_of((long long)t * total, U, num_pairs) + (int)cta_rank;
+      if (st.out_tma && w.mode != 1)
+        tc_epilogue_tma<P_BN>(st, &tmO, stage_smem, mtile, nt * P_BN, phase, warp, lane, tmem_base + acc * P_BN,
+                              tmem_full_bar(acc), ((uint32_t)j >> 1) & 1u, w.mode, self, first);
+      else
+        tc_epilogue<P_BN>(st, mtile, nt * P_BN, phase, 0, warp, lane, tmem_base + acc * P_BN, tmem_full_bar(acc),
+                          ((uint32_t)j >> 1) & 1u, true, w.mode, self, first, 2);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
@@ -540,6 +817,12 @@ static bool use_pair(const StageHost& sh) {
          (d.tiles_b * d.tiles_h * d.tiles_w) >= 2;
 }
 
+static bool tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSNF_NO_TMA_STORE"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return LSNF_ERR_CUDA; }
@@ -574,6 +857,54 @@ int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
       return LSNF_ERR_CUDA;
     }
   }
+  // output map of the hi|lo epilogues of the CTA-pair kernel (tensor stores)
+  sh.dev.out_tma = 0;
+  if (use_pair(sh) && (d.epi == EPI_ACT_HL || d.epi == EPI_GRAD_HL) && tma_store_enabled()) {
+    const cuuint64_t C2 = (cuuint64_t)2 * d.oC, eb = 2;   // channels per position (hi|lo), bytes per element
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+    int kind = 0;
+    if (d.epi == EPI_ACT_HL && sh.first) {                 // [B][k*k][2C]
+      const cuuint64_t kk = (cuuint64_t)sh.k * sh.k;
+      dims[0] = C2; dims[1] = kk; dims[2] = 1; dims[3] = 1; dims[4] = d.B;
+      strides[0] = C2 * eb; strides[1] = C2 * kk * eb; strides[2] = C2 * kk * eb; strides[3] = C2 * kk * eb;
+      box[0] = 64; box[1] = 1; box[2] = 1; box[3] = 1; box[4] = 128;
+      kind = 2;
+    } else if (d.epi == EPI_ACT_HL && d.ms == 2) {         // [B][2H][2W][2C] as (c, px, w, py, b*H + h)
+      const cuuint64_t W = d.Wg, H = d.Hg;
+      dims[0] = C2; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (cuuint64_t)d.B * H;
+      strides[0] = C2 * eb; strides[1] = 2 * C2 * eb; strides[2] = 2 * W * C2 * eb; strides[3] = 4 * W * C2 * eb;
+      box[0] = 64; box[1] = 1; box[2] = d.bW; box[3] = 1; box[4] = d.bB * d.bH;
+      kind = 1;
+    } else if (d.epi == EPI_GRAD_HL && !d.split) {         // [B][H][W][2C]
+      const cuuint64_t W = d.Wg, H = d.Hg;
+      dims[0] = C2; dims[1] = W; dims[2] = H; dims[3] = d.B; dims[4] = 1;
+      strides[0] = C2 * eb; strides[1] = W * C2 * eb; strides[2] = H * W * C2 * eb; strides[3] = (cuuint64_t)d.B * H * W * C2 * eb;
+      box[0] = 64; box[1] = d.bW; box[2] = d.bH; box[3] = d.bB; box[4] = 1;
+      kind = 3;
+    } else if (d.epi == EPI_GRAD_HL && d.split && d.bW >= 2 && d.bH >= 2 && (d.bH % 2) == 0) {
+      // [4 = (py,px)][B][H/2][W/2][2C] as (c, w/2, b*(H/2) + h/2, px, py): strides increase monotonically; the
+      // epilogue permutes its staging rows accordingly
+      const cuuint64_t Wh = d.Wg / 2, Hh = d.Hg / 2;
+      const cuuint64_t plane = (cuuint64_t)d.B * Hh * Wh * C2;
+      dims[0] = C2; dims[1] = Wh; dims[2] = (cuuint64_t)d.B * Hh; dims[3] = 2; dims[4] = 2;
+      strides[0] = C2 * eb; strides[1] = Wh * C2 * eb; strides[2] = plane * eb; strides[3] = 2 * plane * eb;
+      box[0] = 64; box[1] = d.bW / 2; box[2] = d.bB * d.bH / 2; box[3] = 2; box[4] = 2;
+      kind = 4;
+    }
+    if (kind) {
+      CUresult r = enc(&sh.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d.out, dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out) failed with code " + std::to_string((int)r) + " for stage layer " +
+                  std::to_string(sh.layer) + " kind " + std::to_string(sh.kind));
+        return LSNF_ERR_CUDA;
+      }
+      sh.dev.out_tma = kind;
+    }
+  }
+  if (!sh.dev.out_tma) sh.tmO = sh.tmA;   // placeholder, never dereferenced
   sh.maps_ready = true;
   return LSNF_OK;
 }
@@ -609,8 +940,19 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     max_pairs = sms / 2;
   }
-  dim3 grid(2 * std::min(num_tiles, max_pairs), 1, 1);
-  tapgemm_tc2_kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, st);
+  // Stream-K (equal shares of tiles x K blocks per pair, partial accumulators exchanged through L2) pays only when
+  // whole-tile scheduling would leave the pairs badly balanced: it costs a partial-tile round trip per pair.
+  const int total = st.ph[0].ntaps * (st.Ka / BLOCK_K);
+  const int pairs = std::min(num_tiles, max_pairs);
+  const int rounds = (num_tiles + pairs - 1) / pairs;
+  const double static_eff = (double)num_tiles / ((double)rounds * pairs);
+  static int sk_env = -1;
+  if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
+  StageDev launch_st = st;
+  launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && static_eff < 0.85)) && total >= 8 && pairs == max_pairs &&
+                        max_pairs <= 80;
+  dim3 grid(2 * pairs, 1, 1);
+  tapgemm_tc2_kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
