@@ -330,8 +330,8 @@ def main():
     if os.path.exists(tpath):
         try:
             td = json.load(open(tpath))
-            if td.get("workload") == a.workload and td.get("stage") == dom["stage"]:
-                traffic = td.get("dram_bytes_per_launch")
+            if td.get("workload") == a.workload:
+                traffic = td.get("dram_bytes_per_launch_by_stage", {}).get(str(dom["stage"]))
         except Exception:
             traffic = None
     kname = "tapgemm_tc2_kernel (CTA pair, N tile 256)" if dom["block_n"] == 256 else f"tapgemm_tc_kernel<{dom['block_n']}>"

@@ -131,7 +131,12 @@ def test_tensor_core_path_matches_cuda_core_twin_at_full_cifar_config():
         gg = netG._plan(100, torch.device(DEV)).generator_dgrad(x, 0.3)
         out[impl] = (xh.cpu(), gg.cpu())
     assert rel_err(out["tcgen05"][0], out["simt"][0]) < 1e-5
-    assert_grad_close(out["tcgen05"][1], out["simt"][1], what="grad_g tcgen05 vs simt, B=100")
+    # At this width (459 k hidden units per sample) two fp32-accurate forward passes with different summation orders
+    # already disagree on the sign of about one near-zero pre-activation per sample (tools/bwd_diag.py: 76 of 26 M
+    # units of the last hidden layer, every one a factor-5 = 1/leak mismatch), so most samples sit on a kink and
+    # differ by ~1e-3; what must hold is that nothing differs by more than a kink's worth.
+    e = assert_grad_close(out["tcgen05"][1], out["simt"][1], tol=5e-3, what="grad_g tcgen05 vs simt, B=100")
+    assert e.max() < 3e-2
 
 
 def test_cifar_full_config_one_step_against_oracle():

@@ -28,11 +28,12 @@ CASES = {
 }
 
 
-def hl_view(plan, offset, shape_elems):
-    """float32 view of a bf16 hi|lo buffer in the workspace: shape [..., 2C] -> value[..., C]."""
+def hl_view(plan, offset, shape_elems, fp16=False):
+    """float32 view of a 16-bit hi|lo buffer in the workspace: shape [..., 2C] -> value[..., C].
+    Forward activations are fp16 pairs, data-gradient tensors bf16 pairs."""
     n = int(np.prod(shape_elems))
     start = plan._ws_ptr - plan._ws.data_ptr() + offset
-    raw = plan._ws[start:start + 2 * n].view(torch.bfloat16).reshape(shape_elems).float()
+    raw = plan._ws[start:start + 2 * n].view(torch.float16 if fp16 else torch.bfloat16).reshape(shape_elems).float()
     c = shape_elems[-1] // 2
     return raw[..., :c] + raw[..., c:]
 
@@ -98,8 +99,8 @@ def run_case(name, c, impls, out):
                 if info.kind == 0 and info.layer == 0:
                     hh = int(round((info.n_valid // info.out_channels) ** 0.5))
                 shape = (B * hh * hh, 2 * info.out_channels)
-                a = hl_view(ps, info.out_offset, shape)
-                b = hl_view(pt, info.out_offset, shape)
+                a = hl_view(ps, info.out_offset, shape, fp16=info.epilogue == 0)
+                b = hl_view(pt, info.out_offset, shape, fp16=info.epilogue == 0)
             else:
                 n = info.k_splits * B * info.grid_h * info.grid_w * info.n_pad
                 st = ps._ws_ptr - ps._ws.data_ptr() + info.out_offset

@@ -55,7 +55,7 @@ def main():
             for l in range(len(layers) - 1):
                 info = infos[l]
                 hh = pre[l].shape[-1]
-                a = hl_view(plan, info.out_offset, (B, hh, hh, 2 * info.out_channels)).cpu().double().permute(0, 3, 1, 2)
+                a = hl_view(plan, info.out_offset, (B, hh, hh, 2 * info.out_channels), fp16=True).cpu().double().permute(0, 3, 1, 2)
                 mism = (a > 0) != (pre[l] > 0)
                 flips.append(dict(layer=l, n=int(mism.sum()), per_sample=mism.flatten(1).sum(1).tolist(),
                                   abs_pre=[float(v) for v in pre[l][mism].abs()[:6]],
