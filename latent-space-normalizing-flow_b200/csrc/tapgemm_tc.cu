@@ -810,11 +810,15 @@ static bool pair_enabled() {
   if (v < 0) { const char* e = getenv("LSNF_NO_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
-// the CTA-pair kernel serves the wide stages whose M extent gives both CTAs of every pair a tile
+// The CTA-pair kernel serves every stage with 256-wide N tiles.  A stage with a single M tile still uses it: the
+// second CTA of each pair then owns an all-padding tile (its A boxes are out of bounds -> zero fill, no traffic; its
+// stores are clipped), which wastes half of a tensor pipe that such weight-streaming stages leave idle anyway, and
+// buys the persistent schedule, the halved weight traffic per CTA and stream-K over the K range.
 static bool use_pair(const StageHost& sh) {
   const StageDev& d = sh.dev;
-  return pair_enabled() && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 &&
-         (d.tiles_b * d.tiles_h * d.tiles_w) >= 2;
+  const int mtiles = d.tiles_b * d.tiles_h * d.tiles_w;
+  const int total = d.ph[0].ntaps * (d.Ka / BLOCK_K);
+  return pair_enabled() && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 && (mtiles >= 2 || total >= 8);
 }
 
 static bool tma_store_enabled() {
@@ -943,14 +947,16 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
   // Stream-K (equal shares of tiles x K blocks per pair, partial accumulators exchanged through L2) pays only when
   // whole-tile scheduling would leave the pairs badly balanced: it costs a partial-tile round trip per pair.
   const int total = st.ph[0].ntaps * (st.Ka / BLOCK_K);
-  const int pairs = std::min(num_tiles, max_pairs);
-  const int rounds = (num_tiles + pairs - 1) / pairs;
-  const double static_eff = (double)num_tiles / ((double)rounds * pairs);
+  // One K block costs about 1 us of tensor time; the partial-tile round trip of stream-K about 35 of them.
+  const int rounds = (num_tiles + max_pairs - 1) / max_pairs;
+  const long long static_units = (long long)rounds * total;                        // critical path, whole tiles
+  const long long sk_units = ((long long)num_tiles * total + max_pairs - 1) / max_pairs + 35;
   static int sk_env = -1;
   if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
   StageDev launch_st = st;
-  launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && static_eff < 0.85)) && total >= 8 && pairs == max_pairs &&
-                        max_pairs <= 80;
+  launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && sk_units < static_units)) && total >= 8 &&
+                        (long long)num_tiles * total >= 4LL * max_pairs && max_pairs <= 80;
+  const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);
   dim3 grid(2 * pairs, 1, 1);
   tapgemm_tc2_kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
   LSNF_CUDA(cudaGetLastError());
