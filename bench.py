@@ -152,7 +152,7 @@ def cpu_model():
     return "unknown"
 
 
-def run_reference(a, w, rank):
+def run_reference(a, w, rank, out):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure
     Python/torch and does not travel to the GPU box) on the host cores, bounded sample per step."""
     if rank != 0:
@@ -178,10 +178,25 @@ def run_reference(a, w, rank):
             "cpu_baseline": {"value": value, "unit": "latent-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    out.emit(line)
+
+
+class _CleanStdout:
+    """Everything any library prints to stdout (NCCL's version banner, warnings) is diverted to stderr; the one JSON
+    line goes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    out = _CleanStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -199,7 +214,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
-        run_reference(a, w, rank)
+        run_reference(a, w, rank, out)
         return
     if a.warmup < 3:
         a.warmup = 3
@@ -373,7 +388,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_b,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
