@@ -60,43 +60,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons (B200_PROFILING.md recipe).  Started before the warm-up (nvidia-smi takes
+    ~0.2 s to start); every row is time-stamped on arrival and only rows inside the timed window are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 9 and self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        where = "timed region"
+        if not rows:   # region shorter than the sampling period: take the samples closest to it
+            near = sorted((abs(t - (self.t1 or 0)), r) for t, r in self.rows if len(r) >= 9)[:2]
+            rows = [r for _, r in near]
+            where = "nearest samples (timed region shorter than the 50 ms sampling period)"
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        for r in rows:
+            for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None, "window": where}
 
 
 def build_models(w, device):
@@ -196,7 +210,7 @@ class _CleanStdout:
 
 
 def main():
-    out = _CleanStdout()
+    sink = _CleanStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -214,7 +228,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
-        run_reference(a, w, rank, out)
+        run_reference(a, w, rank, sink)
         return
     if a.warmup < 3:
         a.warmup = 3
@@ -230,7 +244,9 @@ def main():
     B, T, nz = w["B"], w["T"], w["nz"]
     x_np, z0_np, _ = synth.inputs(B, nz, 3, w["img"], 1, seed=1 + rank)
     x, z0 = torch.from_numpy(x_np).to(dev), torch.from_numpy(z0_np).to(dev).reshape(B, nz).contiguous()
-    plan = lsnf_b200.langevin_plan(netG, netF, B, dev)
+    from lsnf_b200.plan import default_bwd_passes
+    bwd_passes = default_bwd_passes(noisy_chain=True)   # what sample_langevin_post_z_with_flow uses for noisy chains
+    plan = lsnf_b200.langevin_plan(netG, netF, B, dev, bwd_passes)
     plan.ensure_generator(netG)
     plan.ensure_flow(netF)
     out = torch.empty_like(z0)
@@ -249,19 +265,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(a.warmup):
-        step(i)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(a.warmup):
+        step(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.window_begin()
     e0.record()
     for i in range(a.steps):
         step(a.warmup + i)
     e1.record()
     barrier()
+    sampler.window_end()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -355,8 +373,8 @@ def main():
                 "kernel": f"{kname} stage {dom['stage']} ({dom['kind']} layer {dom['layer']})",
                 "kernel_us": dom["us"], "alg_gflop_per_launch": dom["alg_gflop"],
                 "peak_source": pk["src"] + ", burst bf16 (kernel timed alone)",
-                "mma": "tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulate), 3 passes (hi*hi + hi*lo + lo*hi); "
-                       "algorithmic FLOPs count one pass",
+                "mma": f"tcgen05 kind::f16, fp32 TMEM accumulate; {3 if dom['kind'] == 'fwd' else bwd_passes} pass(es) in this "
+                       "stage (3 = hi*hi + hi*lo + lo*hi of a 16-bit hi/lo split); algorithmic FLOPs count one pass",
                 "share_of_iteration": dom["us"] / step_us, "all_gemm_stages_us": gemm_us, "iteration_us": step_us,
                 "flow_prior_kernel_us": flow_us}
     if a.stage_table:
@@ -374,9 +392,12 @@ def main():
     line = {
         "metric": "langevin_latent_steps_per_sec", "value": value, "unit": "latent-steps/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split/f32-accumulate", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": f"fp16-hi/lo-3pass-fwd+{'fp16-1pass' if bwd_passes == 1 else 'bf16-hi/lo-3pass'}-bwd/f32-accumulate",
+        "data": "synthetic",
         "config": {"workload": a.workload, "dataset": w["dataset"], "nz": nz, "ngf": w["ngf"], "f_width": w["f_width"],
                    "g_l_steps": T, "batch_per_gpu": B, "g_llhd_sigma": w["sigma"], "noise": "in-kernel Philox4x32-10",
+                   "mma_passes": {"forward": 3, "data_gradient": bwd_passes},
                    "l2": f"flushed between timed steps (256 MB written, inside the timed region); per-call working set "
                          f"{plan.ws_bytes / 1e6:.0f} MB",
                    "alg_gflop_per_latent_step": alg_per_ls / 1e9,
@@ -388,7 +409,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_b,
     }
-    out.emit(line)
+    sink.emit(line)
     if world > 1:
         dist.destroy_process_group()
 

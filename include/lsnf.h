@@ -73,7 +73,10 @@ typedef struct lsnf_config {
   int32_t f_coupling;    /* --f_flow_coupling: 1 = affine (default), 0 = additive */
   float leak;            /* --g_activation_leak of the LeakyReLU (0.2) */
   int32_t gemm_impl;     /* lsnf_gemm_impl */
-  int32_t reserved[5];
+  int32_t bwd_passes;    /* tensor-core passes of the data-gradient stages: 0 or 3 = hi/lo split, 3 MMAs per K step
+                            (gradient as exact as the forward pass); 1 = single fp16 pass (gradient to ~2e-4,
+                            z_T still within the 1e-4 budget -- DESIGN.md section 4.1) */
+  int32_t reserved[4];
 } lsnf_config;
 
 /* number of per-step flow parameter pointers expected by lsnf_pack_flow_weights, in this order:
@@ -173,6 +176,7 @@ typedef struct lsnf_stage_info {
   int32_t b_k;           /* columns of the hi half of the packed weight matrix (lo half follows) */
   int32_t b_rows;        /* rows of the packed weight matrix */
   int32_t operand_fp16;  /* operands are fp16 hi|lo (forward stages) rather than bf16 hi|lo (data-gradient stages) */
+  int32_t passes;        /* MMAs per K step: 3 (hi*hi + hi*lo + lo*hi) or 1 (hi*hi only) */
   int64_t a_offset, b_offset, out_offset; /* byte offsets into the workspace */
   int64_t flops;         /* 2*M*N*K over all phases and taps (nominal, padded taps included) */
 } lsnf_stage_info;

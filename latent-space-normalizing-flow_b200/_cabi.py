@@ -21,7 +21,7 @@ class Config(C.Structure):
     _fields_ = [("arch", C.c_int32), ("batch", C.c_int32), ("nz", C.c_int32), ("ngf", C.c_int32), ("nc", C.c_int32),
                 ("f_depth", C.c_int32), ("f_width", C.c_int32), ("f_permutation", C.c_int32),
                 ("f_coupling", C.c_int32), ("leak", C.c_float), ("gemm_impl", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("bwd_passes", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Tap(C.Structure):
@@ -37,7 +37,7 @@ class StageInfo(C.Structure):
                 ("out_off_x", C.c_int32 * LSNF_MAX_PHASES), ("out_phase_split", C.c_int32),
                 ("out_channels", C.c_int32), ("epilogue", C.c_int32), ("k_splits", C.c_int32),
                 ("a_planes", C.c_int32), ("a_h", C.c_int32), ("a_w", C.c_int32), ("tap_gen_k", C.c_int32),
-                ("b_k", C.c_int32), ("b_rows", C.c_int32), ("operand_fp16", C.c_int32),
+                ("b_k", C.c_int32), ("b_rows", C.c_int32), ("operand_fp16", C.c_int32), ("passes", C.c_int32),
                 ("a_offset", C.c_int64), ("b_offset", C.c_int64), ("out_offset", C.c_int64), ("flops", C.c_int64)]
 
 

@@ -48,7 +48,8 @@ int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w
   const long long total = (long long)rows * g.ka;
   const int threads = 256;
   const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
-  const float* scale = st.kind == 0 ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 4) : nullptr;
+  const float* scale = (st.kind == 0 || plan->cfg.bwd_passes == 1)
+                           ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 4) : nullptr;
   pack_stage_kernel<<<blocks, threads, 0, s>>>(w, (uint16_t*)(plan->ws + st.b_off), g, rows, st.ci,
                                                st.info.operand_fp16, scale);
   LSNF_CUDA(cudaGetLastError());
@@ -181,7 +182,8 @@ constexpr int IM2COL_SEG = 32;
 __global__ void __launch_bounds__(128) recon_grad_im2col_kernel(const float* __restrict__ xhat,
                                                                 const float* __restrict__ x,
                                                                 uint16_t* __restrict__ a, int B, int nc, int img,
-                                                                int hin, int k, int s, int p, float inv_sigma2) {
+                                                                int hin, int k, int s, int p, float inv_sigma2,
+                                                                int fp16) {
   extern __shared__ float g[];   // [nc][k][span], span = (seg-1)*s + k
   const int segs = (hin + IM2COL_SEG - 1) / IM2COL_SEG;
   const int seg = blockIdx.x % segs, iy = (blockIdx.x / segs) % hin, b = blockIdx.x / (segs * hin);
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) recon_grad_im2col_kernel(const float* __r
       v = g[(c * k + tap / k) * span + r * s + tap % k];
     }
     uint16_t hi, lo;
-    split16(v, false, hi, lo);   // bf16: operand of the data-gradient stages
+    split16(v, fp16 != 0, hi, lo);   // operand of the data-gradient stages (bf16 hi|lo, or fp16 for one pass)
     a[(row0 + r) * 2 * BLOCK_K + col] = hi;
     a[(row0 + r) * 2 * BLOCK_K + BLOCK_K + col] = lo;
   }
@@ -222,7 +224,7 @@ int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma,
   const size_t smem = (size_t)plan->cfg.nc * y.k * span * 4;
   recon_grad_im2col_kernel<<<plan->cfg.batch * y.hin * segs, 128, smem, s>>>(
       (const float*)(plan->ws + plan->off_xhat), x, (uint16_t*)(plan->ws + plan->off_im2col), plan->cfg.batch,
-      plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p, 1.f / (sigma * sigma));
+      plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p, 1.f / (sigma * sigma), plan->cfg.bwd_passes == 1 ? 1 : 0);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }

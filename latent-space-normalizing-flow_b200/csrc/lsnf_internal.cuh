@@ -55,6 +55,7 @@ struct StageDev {
   int64_t sP, sB, sH, sW, sPos;       // output strides in elements
   int32_t nc, Ho, Wo, pad_;
   int32_t fp16, out_fp16;             // operand / hi|lo-output element format: 1 = fp16, 0 = bf16
+  int32_t passes, out_single;         // MMAs per K step (3 or 1: hi halves only); output written as hi half only
   const float* descale;               // accumulators are multiplied by *descale (weights packed times 2^k), or null
   int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
   float* sk_slots;                    // stream-K: one fp32 partial accumulator [128][256] per CTA of the pair grid

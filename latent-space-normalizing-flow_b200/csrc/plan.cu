@@ -110,7 +110,11 @@ static void fill_dev(lsnf_plan* p, StageHost& st) {
   }
   d.epi = I.epilogue; d.oC = I.out_channels; d.ms = I.out_mul; d.split = I.out_phase_split;
   d.leak = p->cfg.leak;
-  d.fp16 = I.operand_fp16; d.out_fp16 = (I.epilogue == EPI_ACT_HL) ? 1 : 0;
+  d.fp16 = I.operand_fp16; d.passes = I.passes;
+  // single-pass data gradients carry fp16 tensors (hi half only) end to end
+  const bool single_bwd = p->cfg.bwd_passes == 1;
+  d.out_fp16 = (I.epilogue == EPI_ACT_HL || single_bwd) ? 1 : 0;
+  d.out_single = (I.epilogue == EPI_GRAD_HL && single_bwd) ? 1 : 0;
   d.rows_total = (int64_t)p->cfg.batch * I.grid_h * I.grid_w;
   for (int ph = 0; ph < I.n_phases; ++ph) {
     d.ph[ph].ntaps = I.tap_gen_k ? I.tap_gen_k * I.tap_gen_k : I.n_taps[ph];
@@ -143,6 +147,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
   if (c.f_coupling != 0 && c.f_coupling != 1)
     return fail(LSNF_ERR_UNSUPPORTED, "f_flow_coupling must be 0 or 1 (model.py:384-387)");
   if (c.gemm_impl != LSNF_GEMM_TCGEN05 && c.gemm_impl != LSNF_GEMM_SIMT) return fail(LSNF_ERR_INVALID, "bad gemm_impl");
+  if (c.bwd_passes != 0 && c.bwd_passes != 1 && c.bwd_passes != 3) return fail(LSNF_ERR_INVALID, "bwd_passes must be 0, 1 or 3");
 
   lsnf_plan* p = new lsnf_plan();
   p->cfg = c;
@@ -277,7 +282,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
       make_box(I.grid_h, I.grid_w, &I.box_b, &I.box_h, &I.box_w);
       const int total_taps = (st.first || st.last) ? 1 : y.k * y.k;
       const size_t b_rows = (st.first || st.last) ? (size_t)I.n_pad : (size_t)total_taps * I.n_pad;
-      I.operand_fp16 = 1;
+      I.operand_fp16 = 1; I.passes = 3;
       I.a_h = I.grid_h; I.a_w = I.grid_w; I.tap_gen_k = 0; I.b_k = I.k_per_tap; I.b_rows = (int)b_rows;
       st.b_bytes = b_rows * 2 * I.k_per_tap * 2;
       st.b_off = take(st.b_bytes);
@@ -345,6 +350,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
       }
       make_box(I.grid_h, I.grid_w, &I.box_b, &I.box_h, &I.box_w);
       const size_t b_k = st.first ? (size_t)y.k * y.k * y.co : (size_t)I.k_per_tap;
+      I.operand_fp16 = c.bwd_passes == 1 ? 1 : 0; I.passes = c.bwd_passes == 1 ? 1 : 3;
       I.a_h = st.first ? y.k : I.grid_h; I.a_w = st.first ? y.k : I.grid_w;
       I.tap_gen_k = st.first ? y.k : 0; I.b_k = (int)b_k; I.b_rows = (int)b_rows;
       st.b_bytes = b_rows * 2 * b_k * 2;
@@ -443,7 +449,7 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
     d.bias = (st.kind == 0 && !st.last) ? (const float*)(plan->ws + st.bias_off) : nullptr;
     d.sk_slots = (float*)(plan->ws + plan->off_sk_slots);
     d.sk_flags = (int32_t*)(plan->ws + plan->off_sk_flags);
-    d.descale = st.kind == 0 ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 8) : nullptr;
+    d.descale = (st.kind == 0 || plan->cfg.bwd_passes == 1) ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 8) : nullptr;
     d.mask = (st.kind == 1 && !st.first) ? (const __nv_bfloat16*)(plan->ws + st.mask_off) : nullptr;
     if (plan->cfg.gemm_impl == LSNF_GEMM_TCGEN05) {
       int rc = tc_encode_maps(plan, st);

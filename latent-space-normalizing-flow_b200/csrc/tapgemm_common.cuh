@@ -81,7 +81,7 @@ __device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, in
       off = (size_t)rc.b * st.sB + (size_t)rc.m * st.sH + (size_t)rc.n * st.sW;
     uint16_t* o = (uint16_t*)st.out + off + col;
     *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
-    *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
+    if (!st.out_single) *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
   } else {  // EPI_PARTIAL: raw fp32 rows
     const size_t row = ((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n;
     float* o = (float*)st.out + ((size_t)split_idx * st.rows_total + row) * st.n_pad + col;

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
     const bool b_ok = brow_i < st.b_rows && (n0 + bn) < st.n_pad;
     const uint16_t* brw = (const uint16_t*)st.b + (size_t)brow_i * 2 * st.b_k + bcol + kb * BLOCK_K;
     const bool f16 = st.fp16 != 0;
+    const bool one = st.passes == 1;   // single pass: the lo halves are neither written nor read
     for (int slab = 0; slab < BLOCK_K / SIMT_KS; ++slab) {
       {
         __align__(16) uint16_t hi[16], lo[16];
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          As[ah * 16 + i][ar] = a_ok ? join16(hi[i], lo[i], f16) : 0.f;
+          As[ah * 16 + i][ar] = a_ok ? join16(hi[i], one ? (uint16_t)0 : lo[i], f16) : 0.f;
       }
       {
         __align__(16) uint16_t hi[8], lo[8];
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          Bs[bq * 8 + i][bn] = b_ok ? join16(hi[i], lo[i], f16) : 0.f;
+          Bs[bq * 8 + i][bn] = b_ok ? join16(hi[i], one ? (uint16_t)0 : lo[i], f16) : 0.f;
       }
       __syncthreads();
 #pragma unroll 8

@@ -259,7 +259,7 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
           split16(t, out16, hi[q], lo[q]);
         }
         *reinterpret_cast<uint4*>(o16 + cc + j) = *reinterpret_cast<uint4*>(hi);
-        *reinterpret_cast<uint4*>(o16 + lo_off + cc + j) = *reinterpret_cast<uint4*>(lo);
+        if (!st.out_single) *reinterpret_cast<uint4*>(o16 + lo_off + cc + j) = *reinterpret_cast<uint4*>(lo);
       } else {
         *reinterpret_cast<float4*>(o32 + cc + j) = make_float4(f[0], f[1], f[2], f[3]);
         *reinterpret_cast<float4*>(o32 + cc + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -332,11 +332,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         get_tap(st, phase, t, dy, dx, plane, brow, bcol);
         const uint32_t sa = tiles + s * Cfg::STAGE_BYTES;
         const uint32_t sb = sa + 2 * A_TILE_BYTES;
-        mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        const bool three = st.passes != 1;   // single pass: hi halves only
+        mbar_expect_tx(full_bar(s), three ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES / 2);
         tma_load_5d(sa, &tmA, full_bar(s), kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-        tma_load_5d(sa + A_TILE_BYTES, &tmA, full_bar(s), st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
+        if (three) tma_load_5d(sa + A_TILE_BYTES, &tmA, full_bar(s), st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
         tma_load_2d(sb, &tmB, full_bar(s), bcol + kb * BLOCK_K, brow + n0);
-        tma_load_2d(sb + Cfg::B_TILE_BYTES, &tmB, full_bar(s), st.b_k + bcol + kb * BLOCK_K, brow + n0);
+        if (three) tma_load_2d(sb + Cfg::B_TILE_BYTES, &tmB, full_bar(s), st.b_k + bcol + kb * BLOCK_K, brow + n0);
       }
     }
   } else if (warp == 1) {
@@ -354,9 +355,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int k = 0; k < BLOCK_K / 16; ++k) {
           const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
           const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + Cfg::B_TILE_BYTES + k * 32);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          if (st.passes != 1) {
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(empty_bar(s));  // frees the smem slot once the MMAs above have read it
       }
@@ -555,16 +560,17 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_buf + off), "r"(((uint32_t*)hi)[0]),
                    "r"(((uint32_t*)hi)[1]), "r"(((uint32_t*)hi)[2]), "r"(((uint32_t*)hi)[3])
                    : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_buf + off), "r"(((uint32_t*)lo)[0]),
-                   "r"(((uint32_t*)lo)[1]), "r"(((uint32_t*)lo)[2]), "r"(((uint32_t*)lo)[3])
-                   : "memory");
+      if (!st.out_single)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_buf + off), "r"(((uint32_t*)lo)[0]),
+                     "r"(((uint32_t*)lo)[1]), "r"(((uint32_t*)lo)[2]), "r"(((uint32_t*)lo)[3])
+                     : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     epi_bar_sync();
     if (warp == 2 && lane == 0) {
       const int c0 = cb + ch * 64;
       tma_store_5d(tmO, hi_buf, c0, c1, c2, c3, c4);
-      tma_store_5d(tmO, lo_buf, c0 + st.oC, c1, c2, c3, c4);
+      if (!st.out_single) tma_store_5d(tmO, lo_buf, c0 + st.oC, c1, c2, c3, c4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -714,11 +720,12 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = tiles + s * P_STAGE_BYTES;
           const uint32_t sb = sa + 2 * A_TILE_BYTES;
           const uint32_t fb = full_bar(s) & PEER_BIT_MASK;
-          if (leader) mbar_expect_tx(full_bar(s), 2 * P_STAGE_BYTES);
+          const bool three = st.passes != 1;   // single pass: hi halves only
+          if (leader) mbar_expect_tx(full_bar(s), three ? 2 * P_STAGE_BYTES : P_STAGE_BYTES);
           tma2_load_5d(sa, &tmA, fb, kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-          tma2_load_5d(sa + A_TILE_BYTES, &tmA, fb, st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
+          if (three) tma2_load_5d(sa + A_TILE_BYTES, &tmA, fb, st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
           tma2_load_2d(sb, &tmB, fb, bcol + kb * BLOCK_K, brow + nb);
-          tma2_load_2d(sb + P_B_TILE_BYTES, &tmB, fb, st.b_k + bcol + kb * BLOCK_K, brow + nb);
+          if (three) tma2_load_2d(sb + P_B_TILE_BYTES, &tmB, fb, st.b_k + bcol + kb * BLOCK_K, brow + nb);
         }
       }
     }
@@ -746,9 +753,13 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + P_B_TILE_BYTES + k * 32);
-            umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
-            umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            if (st.passes != 1) {
+              umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+              umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma2_bf16(d_tmem, a_hi, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+            }
           }
           umma2_commit_both(empty_bar(s));      // frees the slot in both CTAs
         }

@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from .model import _get, _netF, _netG
-from .plan import get_plan
+from .plan import default_bwd_passes, get_plan
 
 _call_counter = itertools.count()
 
@@ -35,22 +35,24 @@ def make_args(**overrides) -> AttrDict:
     return a
 
 
-def langevin_plan(netG: _netG, netF: _netF, batch: int, device):
+def langevin_plan(netG: _netG, netF: _netF, batch: int, device, bwd_passes: Optional[int] = None):
     return get_plan(arch=netG.dataset, batch=batch, nz=netG.nz, ngf=netG.ngf, nc=netG.nc, f_depth=netF.f_depth,
                     f_width=netF.f_width, f_permutation=netF.f_permutation, f_coupling=netF.f_coupling,
-                    leak=netG.leak, device=device, gemm_impl=netG.gemm_impl)
+                    leak=netG.leak, device=device, gemm_impl=netG.gemm_impl, bwd_passes=bwd_passes)
 
 
 def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbose: bool = False, *,
                                      eps: Optional[torch.Tensor] = None, steps: Optional[int] = None,
                                      with_noise: Optional[bool] = None, seed: Optional[int] = None,
-                                     sample_offset: int = 0):
+                                     sample_offset: int = 0, bwd_passes: Optional[int] = None):
     """z [B,nz,1,1], x [B,nc,H,W] -> (z_k [B,nz,1,1], mean_b|grad_g|, mean_b|grad_f|) as train.py:335 returns them.
 
     ``args`` supplies g_l_steps, g_l_step_size, g_l_with_noise, g_llhd_sigma (train.py:311-326).  ``eps``
     [steps,B,nz,1,1] injects the noise (parity runs); otherwise noise is drawn in-kernel from Philox keyed by
     (seed, sample_offset + b, step), so a sharded batch reproduces the unsharded result bit for bit.  The
     diagnostics use the real batch size (the reference's ``view(args.batch_size, -1)`` breaks on a ragged batch).
+    ``bwd_passes``: tensor-core passes of the reconstruction-gradient GEMMs (``plan.default_bwd_passes``): 1 for
+    chains with noise, 3 for noise-free chains, unless given.
     """
     if not isinstance(netG, _netG) or not isinstance(netF, _netF):
         raise TypeError("netG / netF must be lsnf_b200._netG / _netF instances")
@@ -70,7 +72,10 @@ def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbo
         e = eps.detach().reshape(T, B, netG.nz).contiguous().float()
     if seed is None:
         seed = (int(_get(args, "seed", 1)) << 32) ^ next(_call_counter)
-    plan = langevin_plan(netG, netF, B, z2.device)
+    noisy = noise or eps is not None
+    if bwd_passes is None:
+        bwd_passes = default_bwd_passes(noisy_chain=noisy)
+    plan = langevin_plan(netG, netF, B, z2.device, bwd_passes)
     plan.ensure_generator(netG)
     plan.ensure_flow(netF)
     out, norms = plan.langevin_run(z2, xx, T, s, sigma, with_noise=noise, eps=e, seed=seed,

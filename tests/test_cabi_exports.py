@@ -29,5 +29,5 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.Config) == 4 * 16
     assert C.sizeof(_cabi.Tap) == 16
     # kind..n_phases (12) + n_taps (4) + taps (4*16*4) + out_mul (1) + off_y/x (8) + 11 ints, then 4 int64
-    ints = 12 + 4 + 4 * 16 * 4 + 1 + 8 + 11
+    ints = 12 + 4 + 4 * 16 * 4 + 1 + 8 + 12
     assert C.sizeof(_cabi.StageInfo) == (ints * 4 + 7) // 8 * 8 + 32

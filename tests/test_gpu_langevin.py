@@ -139,6 +139,25 @@ def test_tensor_core_path_matches_cuda_core_twin_at_full_cifar_config():
     assert e.max() < 3e-2
 
 
+def test_cifar_full_config_full_chain_against_oracle():
+    # the headline configuration end to end: nz=128, ngf=128, g_l_steps=40 with injected noise, default pass counts
+    # (3-pass forward, single-pass data gradient); batch of 4 so that the CPU oracle finishes in ~20 s
+    c = dict(dataset="cifar10", nz=128, ngf=128, B=4, sigma=0.3, T=40)
+    args, netG, netF = build(c)
+    x_np, z0_np, eps_np = synth.inputs(4, 128, 3, 32, 40, seed=6)
+    trace = []
+    refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np), to_torch(synth.generator_state("cifar10", 128, 128)),
+                     to_torch(synth.flow_state(128, 64)), refpath.generator_layers("cifar10", 128, 128), depth=5,
+                     steps=40, step_size=0.1, sigma=0.3, eps=torch.from_numpy(eps_np), trace=trace)
+    z0, x, eps = (torch.from_numpy(a).to(DEV) for a in (z0_np, x_np, eps_np))
+    curve = {}
+    for passes in (1, 3):
+        z, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, eps=eps, bwd_passes=passes)
+        curve[passes] = rel_l2(z.cpu(), trace[-1])
+    print("cifar10 T=40 z_T rel-l2 vs oracle: single-pass data gradient %.2e, three-pass %.2e" % (curve[1], curve[3]))
+    assert curve[1] < REL_TOL and curve[3] < REL_TOL
+
+
 def test_cifar_full_config_one_step_against_oracle():
     # one Langevin step of the headline configuration at a batch the CPU oracle finishes in seconds
     c = dict(dataset="cifar10", nz=128, ngf=128, B=8, sigma=0.3, T=2)

@@ -12,7 +12,8 @@ import lsnf_b200
 w = dict(bench.WORKLOADS[os.environ.get("WORKLOAD", "cifar10")])
 dev = torch.device("cuda:0")
 args, netG, netF, gsd, fsd = bench.build_models(w, dev)
-plan = lsnf_b200.langevin_plan(netG, netF, w["B"], dev)
+from lsnf_b200.plan import default_bwd_passes
+plan = lsnf_b200.langevin_plan(netG, netF, w["B"], dev, default_bwd_passes(noisy_chain=True))
 plan.ensure_generator(netG)
 plan.ensure_flow(netF)
 x_np, z0_np, _ = lsnf_b200.synth.inputs(w["B"], w["nz"], 3, w["img"], 1, seed=1)
