@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblsnf_b200.so")
+# LSNF_LIB: load another build of the same ABI (A/B timing of two library versions on one box)
+LIB_PATH = os.environ.get("LSNF_LIB") or os.path.join(_HERE, "_lib", "liblsnf_b200.so")
 _lib = None
 
 LSNF_MAX_TAPS = 16

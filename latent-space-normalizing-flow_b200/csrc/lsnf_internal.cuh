@@ -51,7 +51,9 @@ struct StageDev {
   float leak;
   const float* bias;
   void* out;
-  const __nv_bfloat16* mask;          // saved activation [B][Hg][Wg][2*oC] (EPI_GRAD_HL)
+  uint32_t* mbits;                    // sign bits of a saved activation, [B*H*W][oC/32] words (bit c%32 of word c/32):
+                                      // written by the EPI_ACT_HL stage producing the activation, read by the
+                                      // EPI_GRAD_HL stage that applies LeakyReLU' (train.py:314)
   int64_t sP, sB, sH, sW, sPos;       // output strides in elements
   int32_t nc, Ho, Wo, pad_;
   int32_t fp16, out_fp16;             // operand / hi|lo-output element format: 1 = fp16, 0 = bf16
@@ -60,9 +62,10 @@ struct StageDev {
   int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
   float* sk_slots;                    // stream-K: one fp32 partial accumulator [128][256] per CTA of the pair grid
   int32_t* sk_flags;                  // stream-K: one flag per (CTA, epilogue warp), 0 = empty, 1 = partial ready
-  int32_t sk_enable, pad2_;           // stream-K on/off for this launch
-  int32_t out_tma, pad3_;             // hi|lo output written by TMA tensor stores: 1 up2 forward, 2 first layer,
-                                      // 3 plain gradient, 4 phase-split gradient; 0 = per-thread stores           // 1: equal shares of (tiles x K blocks) per CTA pair; 0: whole tiles, strided
+  int32_t sk_enable, exp;             // stream-K on/off for this launch; experiment switches (0 in production)
+  int32_t out_tma, nst;               // hi|lo output written by TMA tensor stores (1 up2 forward, 2 first layer,
+                                      // 3 plain gradient, 4 phase-split gradient; 0 = per-thread stores); ring depth
+                                      // of this launch (1-CTA kernel)
   PhaseDev ph[LSNF_MAX_PHASES];
 };
 
@@ -74,7 +77,7 @@ struct StageHost {
   int layer = 0;
   int kind = 0;      // 0 fwd, 1 bwd
   int k = 0, s = 0, p = 0, ci = 0, co = 0;  // the ConvTranspose2d this stage belongs to
-  size_t a_off = 0, b_off = 0, out_off = 0, mask_off = 0, bias_off = 0;
+  size_t a_off = 0, b_off = 0, out_off = 0, mbits_off = 0, bias_off = 0;
   size_t b_bytes = 0;
   bool last = false, first = false;
 };
@@ -101,7 +104,7 @@ struct lsnf_plan {
   lsnf::FlowLayout fl;
   // workspace layout (byte offsets)
   size_t ws_bytes = 0;
-  size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
+  size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_mbits[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
   size_t off_bias[8] = {0};
   size_t off_norms = 0, off_wscale = 0, off_dlast = 0;
   int dlast_pad = 0;

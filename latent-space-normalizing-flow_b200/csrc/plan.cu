@@ -216,6 +216,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
       const size_t bytes = (size_t)B * y.hout * y.hout * 2 * y.co * 2;
       p->off_act[l] = take(bytes);
       p->off_gpre[l] = take(bytes);
+      p->off_mbits[l] = take((size_t)B * y.hout * y.hout * y.co / 8);   // LeakyReLU sign bits of act[l]
     }
     for (int l = 0; l < L; ++l) p->off_bias[l] = take((size_t)p->layers[l].co * 4);
     p->off_xhat = take((size_t)B * c.nc * p->img * p->img * 4);
@@ -287,6 +288,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
       st.b_bytes = b_rows * 2 * I.k_per_tap * 2;
       st.b_off = take(st.b_bytes);
       st.out_off = st.last ? p->off_dlast : p->off_act[l];
+      st.mbits_off = st.last ? 0 : p->off_mbits[l];
       st.bias_off = p->off_bias[l];
       I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
       int taps_sum = 0;
@@ -362,7 +364,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         // the consumer (data gradient of layer l-1) reads phase-split when it is a stride-2 layer
         I.out_phase_split = (l - 1 > 0) ? 1 : 0;
         st.out_off = p->off_gpre[l - 1];
-        st.mask_off = p->off_act[l - 1];
+        st.mbits_off = p->off_mbits[l - 1];
       }
       I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
       I.flops = 2LL * B * I.grid_h * I.grid_w * (long long)I.n_valid *
@@ -450,7 +452,7 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
     d.sk_slots = (float*)(plan->ws + plan->off_sk_slots);
     d.sk_flags = (int32_t*)(plan->ws + plan->off_sk_flags);
     d.descale = (st.kind == 0 || plan->cfg.bwd_passes == 1) ? (const float*)(plan->ws + plan->off_wscale + (size_t)st.layer * 16 + 8) : nullptr;
-    d.mask = (st.kind == 1 && !st.first) ? (const __nv_bfloat16*)(plan->ws + st.mask_off) : nullptr;
+    d.mbits = ((st.kind == 0 && !st.last) || (st.kind == 1 && !st.first)) ? (uint32_t*)(plan->ws + st.mbits_off) : nullptr;
     if (plan->cfg.gemm_impl == LSNF_GEMM_TCGEN05) {
       int rc = tc_encode_maps(plan, st);
       if (rc) return rc;

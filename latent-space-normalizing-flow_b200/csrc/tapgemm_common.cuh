@@ -35,11 +35,24 @@ __device__ __forceinline__ void split_pack(const float* v, bool fp16, uint16_t* 
 // NV is 4 or 8; col % NV == 0.  Reference semantics: bias + LeakyReLU of model.py:56-151, and for the data gradient
 // the LeakyReLU derivative autograd applies (train.py:314).  `pre_mask` (optional) holds the NV saved-activation
 // halves already fetched by the caller.
+// word of the sign-bit array that holds output channel `cb` of the activation element at element offset `off`
+// (offsets are multiples of 2*oC: one hi|lo row per position)
+__device__ __forceinline__ uint32_t* act_bits_word(const StageDev& st, size_t off, int cb) {
+  return st.mbits + off / (size_t)(2 * st.oC) * (size_t)(st.oC >> 5) + (cb >> 5);
+}
+__device__ __forceinline__ const uint32_t* grad_bits_row(const StageDev& st, const RowCtx& rc) {
+  return st.mbits + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * (size_t)(st.oC >> 5);
+}
+
+// Returns the NV LeakyReLU sign bits of an EPI_ACT_HL store (bit j = output j is negative), and through `bits_word`
+// the word they belong to (bit position col % 32); 0 / nullptr otherwise.  The caller assembles whole words.
 template <int NV>
-__device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, int split_idx, const RowCtx& rc,
-                                               int col, const float* acc_in, float descale,
-                                               const uint16_t* pre_mask = nullptr) {
-  if (!rc.valid || col >= st.n_pad) return;
+__device__ __forceinline__ uint32_t epilogue_store(const StageDev& st, int phase, int split_idx, const RowCtx& rc,
+                                                   int col, const float* acc_in, float descale,
+                                                   uint32_t** bits_word = nullptr) {
+  if (bits_word) *bits_word = nullptr;
+  if (!rc.valid || col >= st.n_pad) return 0u;
+  uint32_t signs = 0u;
   using Vec = typename std::conditional<NV == 8, uint4, uint2>::type;
   float acc[NV];
 #pragma unroll
@@ -59,18 +72,14 @@ __device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, in
                   (size_t)pos * st.sPos + cb;
     *reinterpret_cast<Vec*>(o) = *reinterpret_cast<Vec*>(hi);
     *reinterpret_cast<Vec*>(o + st.oC) = *reinterpret_cast<Vec*>(lo);
-  } else if (st.epi == EPI_GRAD_HL) {
-    __align__(16) uint16_t mv[NV];
-    if (pre_mask) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) mv[j] = pre_mask[j];
-    } else {
-      const uint16_t* mk = (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + col;
-      *reinterpret_cast<Vec*>(mv) = *reinterpret_cast<const Vec*>(mk);
-    }
+    for (int j = 0; j < NV; ++j) signs |= (uint32_t)(hi[j] >> 15) << j;   // sign of the hi half = sign of the value
+    if (bits_word) *bits_word = act_bits_word(st, (size_t)(o - cb - (uint16_t*)st.out), cb);
+  } else if (st.epi == EPI_GRAD_HL) {
+    const uint32_t mw = __ldg(grad_bits_row(st, rc) + (col >> 5)) >> (col & 31);
     float v[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = (mv[j] & 0x8000u) ? acc[j] * st.leak : acc[j];  // sign bit of the saved activation
+    for (int j = 0; j < NV; ++j) v[j] = ((mw >> j) & 1u) ? acc[j] * st.leak : acc[j];  // sign of the saved activation
     __align__(16) uint16_t hi[NV], lo[NV];
     split_pack<NV>(v, st.out_fp16 != 0, hi, lo);
     size_t off;
@@ -88,6 +97,7 @@ __device__ __forceinline__ void epilogue_store(const StageDev& st, int phase, in
     *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     if (NV == 8) *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
+  return signs;
 }
 
 // tap of iteration `t` of a phase: table entry, or generated for the first layer's data gradient

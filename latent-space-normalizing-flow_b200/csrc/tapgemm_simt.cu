@@ -92,7 +92,14 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const RowCtx rc = tile_row(st, mtile, ty * 8 + i);
-    epilogue_store<4>(st, phase, split, rc, n0 + tx * 4, acc[i], descale);
+    uint32_t* word = nullptr;
+    uint32_t w = epilogue_store<4>(st, phase, split, rc, n0 + tx * 4, acc[i], descale, &word) << (4 * (tx & 7));
+    if (st.epi == EPI_ACT_HL) {   // uniform: 8 lanes (32 channels) assemble one word of LeakyReLU sign bits
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if ((tx & 7) == 0 && word) *word = w;
+    }
   }
 }
 

@@ -25,14 +25,18 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB per hi or lo half
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 
+// The 1-CTA kernel's operand ring is sized per launch (ring_geometry below): a stage holds the hi halves of the A and
+// B tiles, plus the lo halves for a 3-pass stage; short K loops get shallow rings so that several CTAs share an SM
+// and one CTA's prologue / epilogue overlaps another's loads.
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_EXTRA = 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_MAX = 232448;   // 227 KiB
 template <int BN>
 struct TcCfg {
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
   static constexpr int SPAN = BN >= 64 ? BN / 2 : BN;   // columns per epilogue warp
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr bool TMA_EPI = BN >= 128;            // hi|lo outputs may leave through tensor stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +55,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// One lane of a converged warp.  The producer and MMA warps run their loops with ALL lanes (so addresses,
+// descriptors and coordinates stay warp-uniform and live in uniform registers) and only issue under this predicate;
+// issuing from inside an `if (lane == 0)` region makes every operand thread-varying and costs an
+// elect / R2UR.BROADCAST loop around each UTMALDG / UTCHMMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -121,6 +140,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void epi_bar_sync() {   // the 8 epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+}
+
+// element i of a small register array without dynamic indexing (which would push the array to local memory)
+template <int N>
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&a)[N], int i) {
+  uint32_t r = a[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) r = (i == k) ? a[k] : r;
+  return r;
+}
+
+// The column loops of the epilogues are deliberately NOT unrolled: unrolled they made the CTA-pair kernel 240 KB of
+// SASS, far beyond the instruction cache, and the producer / MMA loops kept missing in it.
 // Epilogue of one 128-row accumulator tile.  Warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps w and w+4
 // split the columns.  Row-invariant addressing is hoisted out of the column loop, and the saved-activation signs a
 // data-gradient row needs are fetched BEFORE waiting for the accumulator, i.e. while the main loop still runs.
@@ -153,12 +187,16 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
   uint16_t* o16 = nullptr;
   float* o32 = nullptr;
   const float* bias = nullptr;
-  uint4 mk[SPAN / 8];
+  constexpr int NW = (SPAN + 31) / 32;
+  uint32_t mb[NW];            // LeakyReLU sign bits of this thread's columns (data gradient)
+  uint32_t* obits = nullptr;  // where the sign bits of this thread's outputs go (forward)
   if (ok) {
     if (epi == EPI_ACT_HL) {
       const int pos = col0 / st.oC, cb = col0 % st.oC;
       const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
-      o16 = (uint16_t*)st.out + (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW + (size_t)pos * st.sPos + cb;
+      const size_t off = (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW + (size_t)pos * st.sPos;
+      o16 = (uint16_t*)st.out + off + cb;
+      obits = act_bits_word(st, off, cb);
       bias = st.bias + cb;
     } else if (epi == EPI_GRAD_HL) {
       size_t off;
@@ -168,10 +206,9 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
       else
         off = (size_t)rc.b * st.sB + (size_t)rc.m * st.sH + (size_t)rc.n * st.sW;
       o16 = (uint16_t*)st.out + off + col0;
-      const uint4* mp = reinterpret_cast<const uint4*>(
-          (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + col0);
+      const uint32_t* mp = grad_bits_row(st, rc) + (col0 >> 5);
 #pragma unroll
-      for (int j = 0; j < SPAN / 8; ++j) mk[j] = __ldg(mp + j);
+      for (int j = 0; j < NW; ++j) mb[j] = __ldg(mp + j);
     } else {
       const size_t row = ((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n;
       o32 = (float*)st.out + ((size_t)split * st.rows_total + row) * st.n_pad + col0;
@@ -186,7 +223,7 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
     // helper: raw accumulator -> slot[sk_self], stored COLUMN-major ([256 columns][128 rows]) so that the 32 lanes
     // of a warp (32 consecutive rows) write 128 contiguous bytes per column; then raise this warp's flag
     float* slot = st.sk_slots + ((size_t)sk_self * 256 + c_begin) * BLOCK_M + r;
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < SPAN; cc += CH) {
       uint32_t v[CH];
       const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c_begin + cc);
@@ -217,12 +254,13 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
     __syncwarp();
     __threadfence();
   }
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < SPAN; cc += CH) {
     uint32_t v[CH];
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c_begin + cc);
     if constexpr (CH == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const uint32_t mword = pick_word(mb, cc >> 5);
     if (sk_mode == 2) {
       for (int h = sk_first; h < sk_self; h += sk_stride) {
         const float* slot = st.sk_slots + ((size_t)h * 256 + c_begin + cc) * BLOCK_M + r;
@@ -232,6 +270,7 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
       }
     }
     if (!ok) continue;
+    uint32_t signs = 0u;
 #pragma unroll
     for (int j = 0; j < CH; j += 8) {
       float f[8];
@@ -247,15 +286,16 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
           float t = f[q] + bb[q];
           t = t > 0.f ? t : t * leak;
           split16(t, out16, hi[q], lo[q]);
+          signs |= (uint32_t)(hi[q] >> 15) << ((j + q) & 31);
         }
         *reinterpret_cast<uint4*>(o16 + cc + j) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(o16 + lo_off + cc + j) = *reinterpret_cast<uint4*>(lo);
       } else if (epi == EPI_GRAD_HL) {
-        const uint16_t* mv = reinterpret_cast<const uint16_t*>(&mk[(cc + j) / 8]);
+        const uint32_t mw = mword >> ((cc + j) & 31);
         __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float t = (mv[q] & 0x8000u) ? f[q] * leak : f[q];   // sign bit of the saved activation
+          const float t = ((mw >> q) & 1u) ? f[q] * leak : f[q];   // sign of the saved activation
           split16(t, out16, hi[q], lo[q]);
         }
         *reinterpret_cast<uint4*>(o16 + cc + j) = *reinterpret_cast<uint4*>(hi);
@@ -265,6 +305,9 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
         *reinterpret_cast<float4*>(o32 + cc + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
       }
     }
+    if constexpr (CH == 32) {
+      if (epi == EPI_ACT_HL) obits[cc >> 5] = signs;   // hidden widths are multiples of 64: whole words
+    }
   }
   if (sk_mode == 2) {
     __syncwarp();
@@ -273,22 +316,32 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
   }
 }
 
+template <int BN, bool SINGLE>
+__device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtensorMap* tmO, uint32_t stage_smem,
+                                                int mtile, int n0, int phase, int warp, int lane, uint32_t tmem_acc,
+                                                uint32_t full_bar, uint32_t parity, int sk_mode, int sk_self,
+                                                int sk_first);
+
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ StageDev st) {
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ StageDev st) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = tiles + Cfg::STAGES * Cfg::STAGE_BYTES;
-  // barrier block: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address slot
+  const bool three = st.passes != 1;   // single pass: hi halves only, compact stages
+  const uint32_t nst = (uint32_t)st.nst;
+  const uint32_t a_bytes = three ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+  const uint32_t stage_bytes = a_bytes + (three ? 2 : 1) * Cfg::B_TILE_BYTES;
+  const uint32_t bars = tiles + nst * stage_bytes;
+  // barrier block: full[MAX], empty[MAX], tmem_full, then the TMEM base address slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::STAGES);
-  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 1);
+  auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * TC_MAX_STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 1);
   uint8_t* gen_base = smem_raw + (tiles - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(gen_base + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 1));
+      reinterpret_cast<volatile uint32_t*>(gen_base + nst * stage_bytes + 8 * (2 * TC_MAX_STAGES + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtile = blockIdx.x, n0 = blockIdx.y * BN;
@@ -300,7 +353,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    if (Cfg::TMA_EPI && st.out_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -319,56 +373,77 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===== TMA producer =====
       int b0, h0, w0;
       tile_origin(st, mtile, b0, h0, w0);
+      uint32_t s = 0, par = 0, sa = tiles;
+      int tp = it0 / kblocks, kc = (it0 - tp * kblocks) * BLOCK_K;
+      int dy = 0, dx = 0, plane = 0, brow = 0, bcol = 0;
+      if (it1 > it0) get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
       for (int it = it0; it < it1; ++it) {
-        const int i = it - it0, s = i % Cfg::STAGES;
-        const uint32_t par = (uint32_t)((i / Cfg::STAGES) & 1);
         mbar_wait(empty_bar(s), par ^ 1u);
-        const int t = it / kblocks, kb = it % kblocks;
-        int dy, dx, plane, brow, bcol;
-        get_tap(st, phase, t, dy, dx, plane, brow, bcol);
-        const uint32_t sa = tiles + s * Cfg::STAGE_BYTES;
-        const uint32_t sb = sa + 2 * A_TILE_BYTES;
-        const bool three = st.passes != 1;   // single pass: hi halves only
-        mbar_expect_tx(full_bar(s), three ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES / 2);
-        tma_load_5d(sa, &tmA, full_bar(s), kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-        if (three) tma_load_5d(sa + A_TILE_BYTES, &tmA, full_bar(s), st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-        tma_load_2d(sb, &tmB, full_bar(s), bcol + kb * BLOCK_K, brow + n0);
-        if (three) tma_load_2d(sb + Cfg::B_TILE_BYTES, &tmB, full_bar(s), st.b_k + bcol + kb * BLOCK_K, brow + n0);
+        const uint32_t sb = sa + a_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          tma_load_5d(sa, &tmA, full_bar(s), kc, w0 + dx, h0 + dy, b0, plane);
+          if (three) tma_load_5d(sa + A_TILE_BYTES, &tmA, full_bar(s), st.Ka + kc, w0 + dx, h0 + dy, b0, plane);
+          tma_load_2d(sb, &tmB, full_bar(s), bcol + kc, brow + n0);
+          if (three) tma_load_2d(sb + Cfg::B_TILE_BYTES, &tmB, full_bar(s), st.b_k + bcol + kc, brow + n0);
+        }
+        kc += BLOCK_K;
+        if (kc == st.Ka) {
+          kc = 0; ++tp;
+          if (it + 1 < it1) get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
+        }
+        sa += stage_bytes;
+        if (++s == nst) { s = 0; par ^= 1u; sa = tiles; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc<BN>(st.fp16 != 0);
+      uint32_t s = 0, par = 0, sa = tiles;
       for (int it = it0; it < it1; ++it) {
-        const int i = it - it0, s = i % Cfg::STAGES;
-        const uint32_t par = (uint32_t)((i / Cfg::STAGES) & 1);
         mbar_wait(full_bar(s), par);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tiles + s * Cfg::STAGE_BYTES;
-        const uint32_t sb = sa + 2 * A_TILE_BYTES;
+        const uint64_t da = umma_desc(sa), db = umma_desc(sa + a_bytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
-          const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + Cfg::B_TILE_BYTES + k * 32);
-          if (st.passes != 1) {
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
-          } else {
-            umma_bf16(tmem_base, a_hi, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t a_hi = da + 2 * k, a_lo = a_hi + (A_TILE_BYTES >> 4);
+            const uint64_t b_hi = db + 2 * k, b_lo = b_hi + (Cfg::B_TILE_BYTES >> 4);
+            if (three) {
+              umma_bf16(tmem_base, a_lo, b_hi, idesc, (it > it0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+              umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_bf16(tmem_base, a_hi, b_hi, idesc, (it > it0 || k > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar(s));  // frees the smem slot once the MMAs above have read it
         }
-        umma_commit(empty_bar(s));  // frees the smem slot once the MMAs above have read it
+        sa += stage_bytes;
+        if (++s == nst) { s = 0; par ^= 1u; sa = tiles; }
       }
-      umma_commit(tmem_full_bar);   // accumulator complete
+      if (elect_one()) umma_commit(tmem_full_bar);   // accumulator complete (same lane as the MMAs: elect is deterministic)
     }
   } else {
-    tc_epilogue<BN>(st, mtile, n0, phase, split, warp, lane, tmem_base, tmem_full_bar, 0u, it1 > it0);
+    bool done = false;
+    if constexpr (Cfg::TMA_EPI) {
+      // hi|lo outputs of a wide tile leave through tensor stores; the operand ring is idle once the accumulator is
+      // complete, so its first 32 KiB serve as the staging tile
+      if (st.out_tma) {
+        if (st.out_single)
+          tc_epilogue_tma<BN, true>(st, &tmO, tiles, mtile, n0, phase, warp, lane, tmem_base, tmem_full_bar, 0u, 0, 0, 0);
+        else
+          tc_epilogue_tma<BN, false>(st, &tmO, tiles, mtile, n0, phase, warp, lane, tmem_base, tmem_full_bar, 0u, 0, 0, 0);
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        done = true;
+      }
+    }
+    if (!done) tc_epilogue<BN>(st, mtile, n0, phase, split, warp, lane, tmem_base, tmem_full_bar, 0u, it1 > it0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -388,7 +463,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int P_BN = 256;
 constexpr int P_B_TILE_BYTES = (P_BN / 2) * BLOCK_K * 2;                 // this CTA's half of the weight rows
 constexpr int P_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * P_B_TILE_BYTES;      // 64 KiB per CTA
-constexpr int P_STAGES = 3;
+constexpr int P_STAGES = 3;                                                // 64 KiB stages (hi and lo halves) ...
+constexpr int P_MAX_STAGES = 2 * P_STAGES;                                 // ... or twice as many 32 KiB ones (hi only)
 constexpr int P_EPI_STAGING = 2 * BLOCK_M * 128;                           // hi + lo slab of 128 rows x 64 channels
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_EPI_STAGING + 1024 + 256;   // ring + staging + align + barriers
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;                            // clears the CTA-rank bit of a shared::cluster address
@@ -444,9 +520,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
       "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(L2_EVICT_FIRST)
       : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {   // the 8 epilogue warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-}
 
 // Epilogue of the CTA-pair kernel for the hi|lo outputs, through shared memory and TMA tensor stores.
 // Per-thread 16-byte stores of a thread-per-row layout touch 32 different 1 KB-strided rows per instruction; they
@@ -454,7 +527,15 @@ __device__ __forceinline__ void epi_bar_sync() {   // the 8 epilogue warps only
 // 64-channel slab at a time: warp (quarter, half) converts rows [32*quarter, +32) x channels [32*half, +32) into the
 // 128-byte-swizzled staging tile (hi and lo, 16 KiB each), then one thread issues two 5-D tensor stores (the box
 // scatters rows to their strided / phase-split positions and clips the ragged batch).
-template <int BN>
+// SINGLE (outputs keep only their hi half: the single-pass data gradient): the two 16 KiB buffers alternate between
+// consecutive slabs, so a slab's tensor store drains while the next slab is converted.
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, bool fp16) {
+  if (fp16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BN, bool SINGLE>
 __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtensorMap* tmO, uint32_t stage_smem,
                                                 int mtile, int n0, int phase, int warp, int lane, uint32_t tmem_acc,
                                                 uint32_t full_bar, uint32_t parity, int sk_mode, int sk_self,
@@ -468,17 +549,21 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
   const float leak = st.leak;
   const bool out16 = st.out_fp16 != 0;
   constexpr int NCH = BN / 64;   // 64-channel slabs per tile
-  // saved-activation signs for this thread's 32 channels of every slab (prefetched while the main loop runs)
-  uint4 mk[NCH * 4];
+  // saved-activation signs for this thread's 32 channels of every slab (fetched while the main loop runs), or the
+  // place where the signs of this thread's outputs go
+  uint32_t mb[NCH];
+  uint32_t* obits = nullptr;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) mb[ch] = 0u;
   if (epi == EPI_GRAD_HL && rc.valid) {
-    const uint16_t* mrow = (const uint16_t*)st.mask + (((size_t)rc.b * st.Hg + rc.m) * st.Wg + rc.n) * 2 * st.oC + n0;
+    const uint32_t* mrow = grad_bits_row(st, rc) + (n0 >> 5) + half;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mk[ch * 4 + j] = __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64 + half * 32) + j);
-  } else {
-#pragma unroll
-    for (int j = 0; j < NCH * 4; ++j) mk[j] = make_uint4(0, 0, 0, 0);
+    for (int ch = 0; ch < NCH; ++ch) mb[ch] = __ldg(mrow + 2 * ch);
+  } else if (epi == EPI_ACT_HL && rc.valid) {
+    const int pos = n0 / st.oC;
+    const int mo = rc.m * st.ms + st.ph[phase].mo, no = rc.n * st.ms + st.ph[phase].no;
+    const size_t off = (size_t)rc.b * st.sB + (size_t)mo * st.sH + (size_t)no * st.sW + (size_t)pos * st.sPos;
+    obits = act_bits_word(st, off, n0 % st.oC) + half;
   }
   // tensor-store coordinates of this tile
   int b0, h0, w0;
@@ -498,7 +583,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
   }
   const float* bias = (epi == EPI_ACT_HL) ? st.bias + cb + half * 32 : nullptr;
   const float descale = st.descale ? __ldg(st.descale) : 1.f;
-  const uint32_t hi_buf = stage_smem, lo_buf = stage_smem + 128 * 128;
+  const uint32_t buf0 = stage_smem, buf1 = stage_smem + 128 * 128;
 
   mbar_wait(full_bar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -515,7 +600,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
     __syncwarp();
     __threadfence();
   }
-#pragma unroll
+#pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     const int col = ch * 64 + half * 32;   // column of the accumulator tile
     uint32_t v[32];
@@ -530,50 +615,65 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
           v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(slot + (size_t)j * BLOCK_M));
       }
     }
-    // the previous slab's tensor stores have finished reading the staging tile (the issuing thread waited for
-    // that before arriving here)
+    // SINGLE: this slab's buffer was last used two slabs ago; at most the previous slab's store may still be
+    // reading.  Otherwise the issuing thread already waited for the previous slab's stores before arriving here.
+    const uint32_t hi_buf = SINGLE ? ((ch & 1) ? buf1 : buf0) : buf0;
+    const uint32_t lo_buf = buf1;
+    if (SINGLE && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     epi_bar_sync();
+    uint32_t signs = 0u;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
-      __align__(16) uint16_t hi[8], lo[8];
+      float t[8];
       if (epi == EPI_ACT_HL) {
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(bias + ch * 64 + j));
         const float4 q1 = __ldg(reinterpret_cast<const float4*>(bias + ch * 64 + j + 4));
         const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float t = __uint_as_float(v[j + q]) * descale + bb[q];
-          t = t > 0.f ? t : t * leak;
-          split16(t, out16, hi[q], lo[q]);
+          const float a = __uint_as_float(v[j + q]) * descale + bb[q];
+          t[q] = a > 0.f ? a : a * leak;
+          signs |= (__float_as_uint(t[q]) >> 31) << (j + q);   // rounding to 16 bits keeps the sign
         }
       } else {
-        const uint16_t* mv = reinterpret_cast<const uint16_t*>(&mk[ch * 4 + j / 8]);
+        const uint32_t mw = pick_word(mb, ch) >> j;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float a = __uint_as_float(v[j + q]) * descale;
-          split16((mv[q] & 0x8000u) ? a * leak : a, out16, hi[q], lo[q]);
+          t[q] = ((mw >> q) & 1u) ? a * leak : a;   // sign of the saved activation
         }
       }
       // row r of the slab is 128 B; the 16-byte chunk index is XORed with (row % 8) -- the 128-byte TMA swizzle
       const uint32_t chunk = (uint32_t)(half * 4 + j / 8) ^ (uint32_t)(srow & 7);
       const uint32_t off = (uint32_t)srow * 128u + chunk * 16u;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_buf + off), "r"(((uint32_t*)hi)[0]),
-                   "r"(((uint32_t*)hi)[1]), "r"(((uint32_t*)hi)[2]), "r"(((uint32_t*)hi)[3])
-                   : "memory");
-      if (!st.out_single)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_buf + off), "r"(((uint32_t*)lo)[0]),
-                     "r"(((uint32_t*)lo)[1]), "r"(((uint32_t*)lo)[2]), "r"(((uint32_t*)lo)[3])
+      if constexpr (SINGLE) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_buf + off), "r"(pack2_16(t[0], t[1], out16)),
+                     "r"(pack2_16(t[2], t[3], out16)), "r"(pack2_16(t[4], t[5], out16)),
+                     "r"(pack2_16(t[6], t[7], out16))
                      : "memory");
+      } else {
+        __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) split16(t[q], out16, hi[q], lo[q]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_buf + off), "r"(((uint32_t*)hi)[0]),
+                     "r"(((uint32_t*)hi)[1]), "r"(((uint32_t*)hi)[2]), "r"(((uint32_t*)hi)[3])
+                     : "memory");
+        if (!st.out_single)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_buf + off), "r"(((uint32_t*)lo)[0]),
+                       "r"(((uint32_t*)lo)[1]), "r"(((uint32_t*)lo)[2]), "r"(((uint32_t*)lo)[3])
+                       : "memory");
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     epi_bar_sync();
     if (warp == 2 && lane == 0) {
       const int c0 = cb + ch * 64;
       tma_store_5d(tmO, hi_buf, c0, c1, c2, c3, c4);
-      if (!st.out_single) tma_store_5d(tmO, lo_buf, c0 + st.oC, c1, c2, c3, c4);
+      if (!SINGLE && !st.out_single) tma_store_5d(tmO, lo_buf, c0 + st.oC, c1, c2, c3, c4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (!SINGLE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    if (obits) obits[2 * ch] = signs;   // after the barrier: the store's latency stays off the slab's critical path
   }
   if (sk_mode == 2) {
     __syncwarp();
@@ -643,6 +743,10 @@ __device__ __forceinline__ int sk_pair_of(long long u, long long U, int P) {
 
 // Persistent: one CTA pair per SM pair.  The shared-memory ring keeps streaming across tile boundaries, and the 512
 // TMEM columns hold TWO 256-column accumulators so the epilogue of item i overlaps the main loop of item i+1.
+// DEEP (single-pass stages: hi halves only) splits the same ring memory into twice as many half-sized stages.  The
+// ring geometry is a compile-time constant on purpose: with run-time stage counts / sizes the 3-pass stages measured
+// 6 % slower.
+template <bool DEEP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ StageDev st) {
@@ -651,13 +755,19 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t stage_smem = tiles + P_STAGES * P_STAGE_BYTES;   // 32 KiB epilogue staging (hi, lo slabs)
   const uint32_t bars = stage_smem + P_EPI_STAGING;
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (P_STAGES + s); };
-  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * P_STAGES + a); };
-  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * P_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * P_STAGES + 4);
+  auto empty_bar = [&](int s) { return bars + 8u * (P_MAX_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * P_MAX_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * P_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * P_MAX_STAGES + 4);
   uint8_t* gen_base = smem_raw + (tiles - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      gen_base + P_STAGES * P_STAGE_BYTES + P_EPI_STAGING + 8 * (2 * P_STAGES + 4));
+      gen_base + P_STAGES * P_STAGE_BYTES + P_EPI_STAGING + 8 * (2 * P_MAX_STAGES + 4));
+  // A single-pass stage loads hi halves only: the same ring memory then holds twice as many, half-sized stages --
+  // the bytes in flight, not the stage count, are what hides the L2 latency
+  constexpr bool three = !DEEP;
+  constexpr uint32_t nst = DEEP ? P_MAX_STAGES : P_STAGES;
+  constexpr uint32_t stage_bytes = DEEP ? P_STAGE_BYTES / 2 : P_STAGE_BYTES;
+  constexpr uint32_t b_off = DEEP ? A_TILE_BYTES : 2 * A_TILE_BYTES;
 
   uint32_t cta_rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -677,7 +787,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (st.out_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
-    for (int s = 0; s < P_STAGES; ++s) {
+    for (int s = 0; s < P_MAX_STAGES; ++s) {
       mbar_init(full_bar(s), 1);    // leader's producer arrives once per use (+ the bytes of both CTAs)
       mbar_init(empty_bar(s), 1);   // one multicast commit per use
     }
@@ -699,9 +809,12 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===== TMA producer (both CTAs); completions of both land on the LEADER's full barrier =====
-      uint32_t i = 0;   // running K-block counter: the ring does not drain between items
+      // Nothing but the barrier wait and the copies sits between a slot becoming free and its refill: the ring is
+      // only as deep as shared memory allows, so every cycle spent here shows up as an idle tensor pipe.
+      uint32_t s = 0, par = 0, sa = tiles;   // ring slot, its use parity and address: no drain between items
+      constexpr uint32_t tx_bytes = three ? 2 * P_STAGE_BYTES : P_STAGE_BYTES;   // both CTAs' bytes land on the leader
       for (int j = 0; j < sk.n_items; ++j) {
         const SkItem w = sk.item(j);
         const int t = w.tile;
@@ -710,31 +823,36 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int b0, h0, w0;
         tile_origin(st, mtile, b0, h0, w0);
         const int nb = nt * P_BN + (int)cta_rank * (P_BN / 2);
-        for (int it = w.ka; it < w.kb; ++it, ++i) {
-          const int s = i % P_STAGES;
-          const uint32_t par = (i / P_STAGES) & 1u;
+        int tp = w.ka / kblocks, kc = (w.ka - tp * kblocks) * BLOCK_K;
+        int dy, dx, plane, brow, bcol;
+        get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
+        for (int it = w.ka; it < w.kb; ++it) {
           mbar_wait(empty_bar(s), par ^ 1u);
-          const int tp = it / kblocks, kb = it % kblocks;
-          int dy, dx, plane, brow, bcol;
-          get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
-          const uint32_t sa = tiles + s * P_STAGE_BYTES;
-          const uint32_t sb = sa + 2 * A_TILE_BYTES;
+          const uint32_t sb = sa + b_off;
           const uint32_t fb = full_bar(s) & PEER_BIT_MASK;
-          const bool three = st.passes != 1;   // single pass: hi halves only
-          if (leader) mbar_expect_tx(full_bar(s), three ? 2 * P_STAGE_BYTES : P_STAGE_BYTES);
-          tma2_load_5d(sa, &tmA, fb, kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-          if (three) tma2_load_5d(sa + A_TILE_BYTES, &tmA, fb, st.Ka + kb * BLOCK_K, w0 + dx, h0 + dy, b0, plane);
-          tma2_load_2d(sb, &tmB, fb, bcol + kb * BLOCK_K, brow + nb);
-          if (three) tma2_load_2d(sb + P_B_TILE_BYTES, &tmB, fb, st.b_k + bcol + kb * BLOCK_K, brow + nb);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full_bar(s), tx_bytes);
+            tma2_load_5d(sa, &tmA, fb, kc, w0 + dx, h0 + dy, b0, plane);
+            if (three) tma2_load_5d(sa + A_TILE_BYTES, &tmA, fb, st.Ka + kc, w0 + dx, h0 + dy, b0, plane);
+            tma2_load_2d(sb, &tmB, fb, bcol + kc, brow + nb);
+            if (three) tma2_load_2d(sb + P_B_TILE_BYTES, &tmB, fb, st.b_k + bcol + kc, brow + nb);
+          }
+          kc += BLOCK_K;
+          if (kc == st.Ka) {
+            kc = 0; ++tp;
+            if (it + 1 < w.kb) get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
+          }
+          sa += stage_bytes;
+          if (++s == nst) { s = 0; par ^= 1u; sa = tiles; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       // ===== MMA issuer (leader CTA only): M = 256 over both CTAs, N = 256 =====
       const uint32_t fmt = st.fp16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      uint32_t i = 0;
+      uint32_t s = 0, par = 0, sa = tiles;
       for (int j = 0; j < sk.n_items; ++j) {
         const SkItem w = sk.item(j);
         const uint32_t acc = (uint32_t)j & 1u;
@@ -742,28 +860,30 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(tmem_empty_bar(acc), (((uint32_t)j >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * P_BN;
-        for (int it = w.ka; it < w.kb; ++it, ++i) {
-          const int s = i % P_STAGES;
-          const uint32_t par = (i / P_STAGES) & 1u;
+        for (int it = w.ka; it < w.kb; ++it) {
           mbar_wait(full_bar(s), par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = tiles + s * P_STAGE_BYTES;
-          const uint32_t sb = sa + 2 * A_TILE_BYTES;
+          // descriptors differ only in their 16-byte-unit address field: K step k starts 32 bytes further
+          const uint64_t da = umma_desc(sa), db = umma_desc(sa + b_off);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
-            const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + P_B_TILE_BYTES + k * 32);
-            if (st.passes != 1) {
-              umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
-              umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma2_bf16(d_tmem, a_hi, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t a_hi = da + 2 * k, a_lo = a_hi + (A_TILE_BYTES >> 4);
+              const uint64_t b_hi = db + 2 * k, b_lo = b_hi + (P_B_TILE_BYTES >> 4);
+              if (three) {
+                umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+                umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+              } else {
+                umma2_bf16(d_tmem, a_hi, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+              }
             }
+            umma2_commit_both(empty_bar(s));      // frees the slot in both CTAs
           }
-          umma2_commit_both(empty_bar(s));      // frees the slot in both CTAs
+          sa += stage_bytes;
+          if (++s == nst) { s = 0; par ^= 1u; sa = tiles; }
         }
-        umma2_commit_both(tmem_full_bar(acc));  // this accumulator is complete in both CTAs
+        if (elect_one()) umma2_commit_both(tmem_full_bar(acc));  // this accumulator is complete in both CTAs
       }
     }
   } else {
@@ -778,16 +898,24 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int self = 2 * pair_id + (int)cta_rank;       // slot / flag index of this CTA
       int first = self;
       if (w.mode == 2) first = 2 * sk_pair_of((long long)t * total, U, num_pairs) + (int)cta_rank;
-      if (st.out_tma && w.mode != 1)
-        tc_epilogue_tma<P_BN>(st, &tmO, stage_smem, mtile, nt * P_BN, phase, warp, lane, tmem_base + acc * P_BN,
-                              tmem_full_bar(acc), ((uint32_t)j >> 1) & 1u, w.mode, self, first);
-      else
+      if (st.out_tma && w.mode != 1) {
+        if (st.out_single)
+          tc_epilogue_tma<P_BN, true>(st, &tmO, stage_smem, mtile, nt * P_BN, phase, warp, lane,
+                                      tmem_base + acc * P_BN, tmem_full_bar(acc), ((uint32_t)j >> 1) & 1u, w.mode,
+                                      self, first);
+        else
+          tc_epilogue_tma<P_BN, false>(st, &tmO, stage_smem, mtile, nt * P_BN, phase, warp, lane,
+                                       tmem_base + acc * P_BN, tmem_full_bar(acc), ((uint32_t)j >> 1) & 1u, w.mode,
+                                       self, first);
+      } else
         tc_epilogue<P_BN>(st, mtile, nt * P_BN, phase, 0, warp, lane, tmem_base + acc * P_BN, tmem_full_bar(acc),
                           ((uint32_t)j >> 1) & 1u, true, w.mode, self, first, 2);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
     }
+    // the staging tile must outlive the tensor stores that still read it
+    if (st.out_tma && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -825,11 +953,34 @@ static bool pair_enabled() {
 // second CTA of each pair then owns an all-padding tile (its A boxes are out of bounds -> zero fill, no traffic; its
 // stores are clipped), which wastes half of a tensor pipe that such weight-streaming stages leave idle anyway, and
 // buys the persistent schedule, the halved weight traffic per CTA and stream-K over the K range.
+// Stages whose K loop is only one or two blocks long (the first layer, the last layer's data gradient) are all
+// prologue and epilogue: they run on the 1-CTA kernel with shallow rings and several CTAs per SM instead.
 static bool use_pair(const StageHost& sh) {
   const StageDev& d = sh.dev;
   const int mtiles = d.tiles_b * d.tiles_h * d.tiles_w;
   const int total = d.ph[0].ntaps * (d.Ka / BLOCK_K);
-  return pair_enabled() && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 && (mtiles >= 2 || total >= 8);
+  return pair_enabled() && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 && total >= 3 &&
+         (mtiles >= 2 || total >= 8);
+}
+
+// Ring of the 1-CTA kernel for one launch: stage bytes, depth, dynamic shared memory to request.
+struct RingGeom { int nst; size_t stage_bytes, smem; };
+static RingGeom ring_geometry(const StageDev& d) {
+  const bool three = d.passes != 1;
+  const size_t stage = (size_t)(three ? 2 : 1) * (A_TILE_BYTES + (size_t)d.block_n * BLOCK_K * 2);
+  const int total = d.ph[0].ntaps * (d.Ka / BLOCK_K);
+  const int iters = d.ksplit > 1 ? d.it_per_split : total;
+  // short loops: half an SM's shared memory at most, so two CTAs are resident; long loops: all of it
+  const size_t budget = (iters <= 4 ? TC_SMEM_MAX / 2 : TC_SMEM_MAX) - TC_SMEM_EXTRA;
+  int nst = (int)std::min<size_t>(budget / stage, (size_t)std::min(iters, TC_MAX_STAGES));
+  nst = std::max(nst, 1);
+  while (d.out_tma && nst * stage < 32768) ++nst;   // the tensor-store epilogue stages 32 KiB in the idle ring
+  size_t smem = nst * stage + TC_SMEM_EXTRA;
+  // never more resident CTAs than tensor memory can hold (the allocation of one more would spin)
+  const int tmem_cols = d.block_n < 32 ? 32 : d.block_n;
+  const int tmem_ctas = 512 / tmem_cols;
+  smem = std::max(smem, (size_t)TC_SMEM_MAX / (tmem_ctas + 1) + 16);
+  return {nst, stage, smem};
 }
 
 static bool tma_store_enabled() {
@@ -874,7 +1025,8 @@ int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
   }
   // output map of the hi|lo epilogues of the CTA-pair kernel (tensor stores)
   sh.dev.out_tma = 0;
-  if (use_pair(sh) && (d.epi == EPI_ACT_HL || d.epi == EPI_GRAD_HL) && tma_store_enabled()) {
+  const bool wide_single = d.block_n >= 128 && d.n_pad % d.block_n == 0 && d.ksplit == 1;   // 1-CTA kernel, wide N tile
+  if ((use_pair(sh) || wide_single) && (d.epi == EPI_ACT_HL || d.epi == EPI_GRAD_HL) && tma_store_enabled()) {
     const cuuint64_t C2 = (cuuint64_t)2 * d.oC, eb = 2;   // channels per position (hi|lo), bytes per element
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
@@ -924,17 +1076,24 @@ int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
   return LSNF_OK;
 }
 
+static int exp_flags() {   // experiment switches (tools/exp_epi.py); 0 in production
+  const char* e = getenv("LSNF_EXP");
+  return e ? atoi(e) : 0;
+}
+
 template <int BN>
 static int launch_bn(const StageHost& sh, cudaStream_t s) {
-  using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
     attr_set = true;
   }
-  const StageDev& st = sh.dev;
+  StageDev st = sh.dev;
+  st.exp = exp_flags();
+  const RingGeom g = ring_geometry(st);
+  st.nst = g.nst;
   dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, st.nphase * st.ksplit);
-  tapgemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(sh.tmA, sh.tmB, st);
+  tapgemm_tc_kernel<BN><<<grid, TC_THREADS, g.smem, s>>>(sh.tmA, sh.tmB, sh.tmO, st);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -942,7 +1101,8 @@ static int launch_bn(const StageHost& sh, cudaStream_t s) {
 static int launch_pair(const StageHost& sh, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     attr_set = true;
   }
   const StageDev& st = sh.dev;
@@ -965,11 +1125,15 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
   static int sk_env = -1;
   if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
   StageDev launch_st = st;
+  launch_st.exp = exp_flags();
   launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && sk_units < static_units)) && total >= 8 &&
                         (long long)num_tiles * total >= 4LL * max_pairs && max_pairs <= 80;
   const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);
   dim3 grid(2 * pairs, 1, 1);
-  tapgemm_tc2_kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
+  if (st.passes == 1)
+    tapgemm_tc2_kernel<true><<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
+  else
+    tapgemm_tc2_kernel<false><<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_gpu36.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/t_gpu36.log
+timeout 300 python tools/exp_epi.py 0 3 4 5 6 > gpurun_out/exp36.json 2> gpurun_out/exp36.err; echo "exp rc=$?"; cat gpurun_out/exp36.json | tr -d '\n'; echo
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --stage-table gpurun_out/stages_cifar36.json > gpurun_out/bench_cifar36.json 2> gpurun_out/bench_cifar36.err; echo "bench rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_cifar36.json')); print(round(d['value']), 'ls/s', round(d['roofline']['iteration_us'],1), 'us/iter', d['clocks'])
+s=json.load(open('gpurun_out/stages_cifar36.json')); print([round(x['us'],1) for x in s['stages']], s['flow_prior_kernel_us'])"
