@@ -230,6 +230,182 @@ int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The two kernels above fused for the Langevin loop (train.py:312-314 back to back): one CTA owns a TR x TC tile of
+// last-layer input positions.  It stages the direct-product rows of the tile and a 2-position halo in shared memory
+// (coalesced 128-bit reads; the per-position stride is padded to an odd word count so the tap gathers that follow
+// are bank-conflict free), computes x_hat and the loss-gradient seed for the output window the tile's taps touch,
+// and writes the tile's 64-column im2col rows.  x_hat is written by the tile that owns pixel (oy/s, ox/s); the tap
+// summation order equals last_gather_tanh_kernel's, so x_hat is bit-identical to the unfused path.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FUSE_HALO = 2;   // ceil((k-1)/s) for both supported geometries (k3/s1, k4/s2)
+// x / d for the small index ranges of this kernel (x * d < 2^32) as one multiply-high: the kernel is all index
+// arithmetic, and hardware-less 32-bit division made it instruction-bound
+struct FastDiv {
+  uint32_t d, m;
+  __device__ __forceinline__ explicit FastDiv(int d_) : d((uint32_t)d_), m(d_ > 1 ? 0xFFFFFFFFu / (uint32_t)d_ + 1u : 0u) {}
+  __device__ __forceinline__ int div(int x) const { return d > 1 ? (int)__umulhi((uint32_t)x, m) : x; }
+};
+
+template <int K, int S>
+__global__ void __launch_bounds__(256) last_fused_kernel(const float* __restrict__ d, const float* __restrict__ bias,
+                                                         const float* __restrict__ x, float* __restrict__ xhat,
+                                                         uint16_t* __restrict__ a, int B, int nc, int img, int hin,
+                                                         int p, int n_pad, int TR, int TC, float inv_sigma2, int fp16,
+                                                         int write_lo) {
+  extern __shared__ float fs[];
+  constexpr int T = (K + S - 1) / S;
+  const int tiles_c = (hin + TC - 1) / TC, tiles_r = (hin + TR - 1) / TR;
+  const int tc = blockIdx.x % tiles_c, tr = (blockIdx.x / tiles_c) % tiles_r, b = blockIdx.x / (tiles_c * tiles_r);
+  const int r0 = tr * TR, c0 = tc * TC;
+  const int nr = min(TR, hin - r0), ncol = min(TC, hin - c0);
+  const int DW = TC + 2 * FUSE_HALO, DH = TR + 2 * FUSE_HALO, PS = n_pad + 1;
+  const int GH = (TR - 1) * S + K, GW = (TC - 1) * S + K;
+  float* Dt = fs;                         // [DH][DW][PS]
+  float* G = fs + (size_t)DH * DW * PS;   // [nc][GH][GW]
+  const int tid = threadIdx.x;
+  const int qs = n_pad == 32 ? 3 : 4;     // log2 of the float4 count per position (n_pad is 32 or 64)
+  const int dr0 = max(0, r0 - FUSE_HALO), dr1 = min(hin, r0 + nr + FUSE_HALO);
+  const int dc0 = max(0, c0 - FUSE_HALO), dc1 = min(hin, c0 + ncol + FUSE_HALO);
+  const int dwc = dc1 - dc0;
+  const FastDiv by_dwc(dwc), by_gw(GW), by_gwh(GW * GH), by_ncol(ncol);
+  // All global reads of the CTA are issued here, four independent loads per thread at a time: the target pixels of
+  // the output window go to G, which the next phase overwrites in place with the seed; then the direct-product rows
+  // (tile + halo, clipped to the grid).
+  constexpr int U = 4;
+  const int oy_lo = r0 * S - p, ox_lo = c0 * S - p;
+  const int nwin = nc * GH * GW;
+  for (int i0 = tid; i0 < nwin; i0 += U * blockDim.x) {
+    float xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int c = by_gwh.div(i), rem = i - c * GW * GH, yy = by_gw.div(rem), xx = rem - yy * GW;
+      const int oy = oy_lo + yy, ox = ox_lo + xx;
+      xv[u] = (i < nwin && oy >= 0 && oy < img && ox >= 0 && ox < img)
+                  ? __ldg(x + (((size_t)b * nc + c) * img + oy) * img + ox) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < nwin) G[i] = xv[u];
+    }
+  }
+  const int nd = ((dr1 - dr0) * dwc) << qs;
+  const float* dbase = d + ((size_t)b * hin * hin) * n_pad;
+  for (int i0 = tid; i0 < nd; i0 += U * blockDim.x) {
+    float4 v[U];
+    int so[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      so[u] = -1;
+      if (i < nd) {
+        const int q = i & ((1 << qs) - 1), pos = i >> qs;
+        const int row = by_dwc.div(pos), cl = pos - row * dwc;
+        const int ix = dc0 + cl, iy = dr0 + row;
+        v[u] = __ldcg(reinterpret_cast<const float4*>(dbase + ((size_t)iy * hin + ix) * n_pad) + q);
+        so[u] = ((iy - (r0 - FUSE_HALO)) * DW + (ix - (c0 - FUSE_HALO))) * PS + 4 * q;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (so[u] >= 0) {
+        float* o = Dt + so[u];
+        o[0] = v[u].x; o[1] = v[u].y; o[2] = v[u].z; o[3] = v[u].w;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- x_hat and the seed g = (x_hat - x) / sigma^2 * (1 - x_hat^2) on the output window of the tile ----
+  for (int i = tid; i < nwin; i += blockDim.x) {
+    const int c = by_gwh.div(i), rem = i - c * GW * GH, yy = by_gw.div(rem), xx = rem - yy * GW;
+    const int oy = oy_lo + yy, ox = ox_lo + xx;
+    float g = 0.f;
+    if (oy >= 0 && oy < img && ox >= 0 && ox < img) {
+      const int ky0 = (oy + p) % S, kx0 = (ox + p) % S;
+      // local coordinates of the tap (ky0, kx0) in the staged tile; tap (e, f) lies e, f positions before it
+      const int ly = (oy + p - ky0) / S - (r0 - FUSE_HALO), lx = (ox + p - kx0) / S - (c0 - FUSE_HALO);
+      const int gy = (oy + p - ky0) / S, gx = (ox + p - kx0) / S;
+      float acc = bias[c];
+      float v[T * T];
+#pragma unroll
+      for (int e = 0; e < T; ++e) {
+#pragma unroll
+        for (int f = 0; f < T; ++f) {
+          const int ky = ky0 + S * e, kx = kx0 + S * f;
+          const int iy = gy - e, ix = gx - f;
+          const bool ok = ky < K && kx < K && iy >= 0 && ix >= 0 && iy < hin && ix < hin;
+          v[e * T + f] = ok ? Dt[((ly - e) * DW + (lx - f)) * PS + (ky * K + kx) * nc + c] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T * T; ++t) acc += v[t];
+      const float xh = tanhf(acc);
+      const int iyo = oy / S, ixo = ox / S;   // the tile that owns this pixel writes x_hat
+      if (iyo >= r0 && iyo < r0 + nr && ixo >= c0 && ixo < c0 + ncol)
+        xhat[(((size_t)b * nc + c) * img + oy) * img + ox] = xh;
+      g = (xh - G[i]) * inv_sigma2 * (1.f - xh * xh);
+    }
+    G[i] = g;
+  }
+  __syncthreads();
+  // ---- im2col rows of the tile: A[pos][tap*nc + c] = g[c][iy*s - p + ky][ix*s - p + kx] ----
+  // eight threads per position, eight columns (one 16-byte store per half) per thread; a thread's columns are fixed,
+  // so their offsets into the seed window are computed once
+  const int sub = tid & 7;
+  int goff[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = 8 * sub + j;
+    const int tap = col / nc, c = col % nc;
+    goff[j] = col < K * K * nc ? (c * GH + tap / K) * GW + tap % K : -1;
+  }
+  const bool f16 = fp16 != 0;
+  for (int pos = tid >> 3; pos < nr * ncol; pos += blockDim.x >> 3) {
+    const int r = by_ncol.div(pos), cc = pos - r * ncol;
+    const int base = r * S * GW + cc * S;
+    __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split16(goff[j] >= 0 ? G[goff[j] + base] : 0.f, f16, hi[j], lo[j]);
+    uint16_t* row = a + (((size_t)b * hin + r0 + r) * hin + c0 + cc) * 2 * BLOCK_K + 8 * sub;
+    *reinterpret_cast<uint4*>(row) = *reinterpret_cast<const uint4*>(hi);
+    if (write_lo) *reinterpret_cast<uint4*>(row + BLOCK_K) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s) {
+  const auto& y = plan->layers[plan->n_layers - 1];
+  const int n_pad = plan->dlast_pad;
+  const int TC = std::min(32, y.hin), TR = std::min(n_pad <= 32 ? 8 : 4, y.hin);
+  const int DW = TC + 2 * FUSE_HALO, DH = TR + 2 * FUSE_HALO;
+  const int GH = (TR - 1) * y.s + y.k, GW = (TC - 1) * y.s + y.k;
+  const size_t smem = ((size_t)DH * DW * (n_pad + 1) + (size_t)plan->cfg.nc * GH * GW) * 4;
+  const int tiles = ((y.hin + TR - 1) / TR) * ((y.hin + TC - 1) / TC);
+  const float* d = (const float*)(plan->ws + plan->off_dlast);
+  const float* bias = (const float*)(plan->ws + plan->off_bias[plan->n_layers - 1]);
+  float* xh = (float*)(plan->ws + plan->off_xhat);
+  uint16_t* a = (uint16_t*)(plan->ws + plan->off_im2col);
+  const int one = plan->cfg.bwd_passes == 1 ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  if (smem > 160 * 1024) { set_error("fused last-layer kernel: tile does not fit shared memory"); return LSNF_ERR_INVALID; }
+  if (y.k == 3 && y.s == 1)
+    last_fused_kernel<3, 1><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
+                                                                      plan->img, y.hin, y.p, n_pad, TR, TC,
+                                                                      1.f / (sigma * sigma), one, !one);
+  else
+    last_fused_kernel<4, 2><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
+                                                                      plan->img, y.hin, y.p, n_pad, TR, TC,
+                                                                      1.f / (sigma * sigma), one, !one);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // split-K partials [S][B][nzp] -> grad_z [B][nz]  (standalone lsnf_generator_dgrad only; the Langevin loop
 // folds this sum into the update kernel)
 // ---------------------------------------------------------------------------------------------------

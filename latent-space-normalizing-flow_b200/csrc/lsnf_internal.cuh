@@ -167,6 +167,7 @@ int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
 int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);
 int launch_last_gather(const lsnf_plan* plan, cudaStream_t s);
 int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
+int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
 int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s);
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                      const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,

@@ -593,8 +593,8 @@ extern "C" int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad
 
 extern "C" int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps) {
   if (!plan) return 0;
-  // per step: L forward + gather/tanh + im2col + L data-gradient + flow + update; once: split_z
-  return 1 + steps * (2 * plan->n_layers + 4);
+  // per step: L forward + fused gather/tanh/seed/im2col + L data-gradient + flow + update; once: split_z
+  return 1 + steps * (2 * plan->n_layers + 3);
 }
 
 // the g_l_steps loop on stream s: inputs are the workspace copies of z and x
@@ -659,10 +659,8 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
       if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
       tr.mark(("forward layer " + std::to_string(l)).c_str());
     }
-    if ((rc = launch_last_gather(plan, s))) return rc;
-    tr.mark("gather + tanh");
-    if ((rc = launch_recon_grad_im2col(plan, x, sigma, s))) return rc;
-    tr.mark("recon grad + im2col");
+    if ((rc = launch_last_fused(plan, x, sigma, s))) return rc;
+    tr.mark("gather + tanh + recon grad + im2col");
     for (int i = plan->n_layers; i < 2 * plan->n_layers; ++i) {
       if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
       tr.mark(("dgrad layer " + std::to_string(plan->stages[i].layer)).c_str());

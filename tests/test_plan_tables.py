@@ -173,5 +173,5 @@ def test_compute_entry_points_fail_loudly_without_binding():
     assert lib.lsnf_generator_forward(h, None, None, None) == -3          # LSNF_ERR_STATE: not bound
     assert b"bind" in lib.lsnf_last_error()
     assert lib.lsnf_workspace_bytes(h) > 0
-    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 4)
+    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 3)
     lib.lsnf_plan_destroy(h)
