@@ -62,7 +62,7 @@ struct StageDev {
   int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
   float* sk_slots;                    // stream-K: one fp32 partial accumulator [128][256] per CTA of the pair grid
   int32_t* sk_flags;                  // stream-K: one flag per (CTA, epilogue warp), 0 = empty, 1 = partial ready
-  int32_t sk_enable, exp;             // stream-K on/off for this launch; experiment switches (0 in production)
+  int32_t sk_enable, pad2_;           // stream-K on/off for this launch
   int32_t out_tma, nst;               // hi|lo output written by TMA tensor stores (1 up2 forward, 2 first layer,
                                       // 3 plain gradient, 4 phase-split gradient; 0 = per-thread stores); ring depth
                                       // of this launch (1-CTA kernel)

@@ -215,14 +215,7 @@ __device__ __forceinline__ void tc_epilogue(const StageDev& st, int mtile, int n
     }
   }
   const float descale = st.descale ? __ldg(st.descale) : 1.f;
-  if (have_acc) {
-    if (st.exp & 1) {   // experiment: one polling thread, the others block at the named barrier
-      if (warp == 2 && lane == 0) mbar_wait(full_bar, parity);
-      epi_bar_sync();
-    } else {
-      mbar_wait(full_bar, parity);
-    }
-  }
+  if (have_acc) mbar_wait(full_bar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!active) return;
   const int ewarp = warp - 2;
@@ -592,12 +585,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const StageDev& st, const CUtens
   const float descale = st.descale ? __ldg(st.descale) : 1.f;
   const uint32_t buf0 = stage_smem, buf1 = stage_smem + 128 * 128;
 
-  if (st.exp & 1) {
-    if (warp == 2 && lane == 0) mbar_wait(full_bar, parity);
-    epi_bar_sync();
-  } else {
-    mbar_wait(full_bar, parity);
-  }
+  mbar_wait(full_bar, parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (sk_mode == 2) {
     if (lane == 0) {
@@ -975,11 +963,6 @@ static bool use_pair(const StageHost& sh) {
          (mtiles >= 2 || total >= 8);
 }
 
-static int exp_flags() {   // experiment switches (tools/exp_epi.py); 0 in production
-  const char* e = getenv("LSNF_EXP");
-  return e ? atoi(e) : 0;
-}
-
 // Ring of the 1-CTA kernel for one launch: stage bytes, depth, dynamic shared memory to request.
 struct RingGeom { int nst; size_t stage_bytes, smem; };
 static RingGeom ring_geometry(const StageDev& d) {
@@ -991,7 +974,6 @@ static RingGeom ring_geometry(const StageDev& d) {
   const size_t budget = (iters <= 4 ? TC_SMEM_MAX / 2 : TC_SMEM_MAX) - TC_SMEM_EXTRA;
   int nst = (int)std::min<size_t>(budget / stage, (size_t)std::min(iters, TC_MAX_STAGES));
   nst = std::max(nst, 1);
-  if ((exp_flags() & 64) && d.block_n <= 64) nst = 1;   // experiment: one stage, three CTAs per SM
   while (d.out_tma && nst * stage < 32768) ++nst;   // the tensor-store epilogue stages 32 KiB in the idle ring
   size_t smem = nst * stage + TC_SMEM_EXTRA;
   // never more resident CTAs than tensor memory can hold (the allocation of one more would spin)
@@ -1102,7 +1084,6 @@ static int launch_bn(const StageHost& sh, cudaStream_t s) {
     attr_set = true;
   }
   StageDev st = sh.dev;
-  st.exp = exp_flags();
   const RingGeom g = ring_geometry(st);
   st.nst = g.nst;
   dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, st.nphase * st.ksplit);
@@ -1138,7 +1119,6 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
   static int sk_env = -1;
   if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
   StageDev launch_st = st;
-  launch_st.exp = exp_flags();
   launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && sk_units < static_units)) && total >= 8 &&
                         (long long)num_tiles * total >= 4LL * max_pairs && max_pairs <= 80;
   const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);

@@ -62,6 +62,31 @@ def test_langevin_matches_reference_fixture(name, impl):
     assert torch.equal(z0.cpu(), torch.from_numpy(g["z0"])), "inputs must not be modified"
 
 
+@pytest.mark.parametrize("name", ["svhn_small", "cifar_small", "celeba_small"])
+def test_loop_equals_composition_of_the_single_entry_points(name):
+    # lsnf_langevin_run fuses the last layer's gather/tanh, the loss-gradient seed and its im2col into one kernel and
+    # sums the split-K partials inside the update; one iteration must equal forward -> dgrad -> flow -> update called
+    # one by one through the C ABI (same tap-GEMM stages, same LeakyReLU sign bits, same summation orders)
+    g = load_golden(name)
+    c = g["config"]
+    args, netG, netF = build(c)
+    plan = lsnf_b200.langevin_plan(netG, netF, c["B"], torch.device(DEV), bwd_passes=3)
+    plan.ensure_generator(netG)
+    plan.ensure_flow(netF)
+    z0 = torch.from_numpy(g["z0"]).to(DEV).reshape(c["B"], c["nz"]).contiguous()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    eps = torch.from_numpy(g["eps"]).to(DEV).reshape(-1, c["B"], c["nz"])[:1].contiguous()
+    z_loop, norms_loop = plan.langevin_run(z0, x, 1, args.g_l_step_size, c["sigma"], eps=eps)
+    xh = plan.generator_forward(z0)
+    gg = plan.generator_dgrad(x, c["sigma"])
+    _, _, _, gf = plan.flow_forward(z0, want_grad=True)
+    z_step = z0.clone()
+    norms = plan.langevin_update(z_step, gg, gf, args.g_l_step_size, eps=eps[0])
+    assert rel_err(xh.cpu(), g["x_hat"]) < REL_TOL
+    assert rel_l2(z_loop.cpu(), z_step.cpu()) < 1e-6 and rel_err(z_loop.cpu(), z_step.cpu()) < 1e-5
+    assert torch.allclose(norms_loop.cpu(), norms.cpu(), rtol=1e-5)
+
+
 def test_langevin_long_chain_against_oracle_divergence_curve():
     # 20 steps at the SVHN training configuration shape (ngf reduced for CPU-oracle time); the per-step error
     # curve must stay inside the tolerance, not only the end point (hard parts)

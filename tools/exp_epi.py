@@ -1,5 +1,7 @@
-"""Times single generator stages under the LSNF_EXP experiment switches:  python tools/exp_epi.py
-(1 skip mask loads, 2 skip tensor stores, 4 single-buffer staging, 8 skip conversion, 32 shallow ring)."""
+"""Times single generator stages, one synchronised launch at a time:  python tools/exp_epi.py [stage ...]
+EXPS lists values of the LSNF_EXP environment variable to time each stage under (a hook for temporary experiment
+switches in the kernels; the library ignores it otherwise).  With LSNF_LIB pointing at another build of the library
+this gives A/B timings of two builds on one box (tools/run_ab3.sh)."""
 import json
 import os
 import sys
@@ -39,7 +41,7 @@ def time_stage(i, reps=15):
     return ts[len(ts) // 2]
 
 
-variants = [int(a) for a in os.environ.get("EXPS", "0 1 2 3 4 8 10 32 36").split()]
+variants = [int(a) for a in os.environ.get("EXPS", "0").split()]
 stages = [int(a) for a in sys.argv[1:]] or list(range(len(plan.stages())))
 res = {}
 for i in stages:

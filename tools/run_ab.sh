@@ -1,7 +1,12 @@
 #!/bin/bash
-# A/B of two library builds on the same box: tools/_ab/liblsnf_old.so against the in-tree build
 mkdir -p gpurun_out
-for i in 1 2 3; do
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_gpu_ab.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/t_gpu39.log
+for r in 1 2; do
+for v in old new; do
+  if [ $v = new ]; then unset LSNF_LIB; else export LSNF_LIB=$PWD/tools/_ab/liblsnf_$v.so; fi
+  echo -n "$v: "; EXPS="0" timeout 300 python tools/exp_epi.py 2>gpurun_out/ab_$v.err | tr -d '\n'; echo
+done; done
+for i in 1 2; do
 for v in old new; do
   if [ $v = old ]; then export LSNF_LIB=$PWD/tools/_ab/liblsnf_old.so; else unset LSNF_LIB; fi
   timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --stage-table gpurun_out/stages_ab_$v$i.json > gpurun_out/bench_ab_$v$i.json 2> gpurun_out/bench_ab_$v$i.err || echo "bench $v rc=$?"
