@@ -188,6 +188,26 @@ int lsnf_plan_stage_info(const lsnf_plan* plan, int32_t index, lsnf_stage_info* 
 int lsnf_plan_pack_index(const lsnf_plan* plan, int32_t index, int32_t ci, int32_t co, int32_t ky, int32_t kx,
                          int64_t* row, int64_t* col);
 
+/* How the tcgen05 path launches stage `index` on a device with `num_sms` SMs: which kernel, grid, operand ring and
+ * shared memory, resident CTAs per SM, tensor-store map kind, stream-K.  Host only (no device, no bound workspace
+ * needed): the CPU tests check the launch geometry of every BASELINE configuration against the hardware limits
+ * (227 KiB shared memory per CTA, 512 TMEM columns per SM) with it. */
+#define LSNF_KERNEL_SINGLE 0 /* tapgemm_tc_kernel<block_n>: one CTA per tile, ring sized per launch */
+#define LSNF_KERNEL_PAIR 1   /* tapgemm_tc2_kernel: persistent CTA pairs (cta_group::2), N tile 256 */
+typedef struct lsnf_launch_info {
+  int32_t kernel;                 /* LSNF_KERNEL_* */
+  int32_t grid_x, grid_y, grid_z, block;
+  int32_t ring_stages;            /* depth of the shared-memory operand ring */
+  int32_t stage_bytes;            /* bytes of one ring stage (per CTA) */
+  int32_t smem_bytes;             /* dynamic shared memory requested per CTA */
+  int32_t ctas_per_sm;            /* CTAs that fit one SM with that request */
+  int32_t tmem_columns;           /* TMEM columns one CTA allocates */
+  int32_t tma_store;              /* 0 per-thread stores, 1..4 tensor-store map kind of the 16-bit output */
+  int32_t stream_k;               /* 1 if the K range of tiles is split across CTA pairs */
+  int32_t reserved[4];
+} lsnf_launch_info;
+int lsnf_plan_stage_launch_info(const lsnf_plan* plan, int32_t index, int32_t num_sms, lsnf_launch_info* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,15 @@ class StageInfo(C.Structure):
                 ("a_offset", C.c_int64), ("b_offset", C.c_int64), ("out_offset", C.c_int64), ("flops", C.c_int64)]
 
 
+class LaunchInfo(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("grid_x", C.c_int32), ("grid_y", C.c_int32), ("grid_z", C.c_int32),
+                ("block", C.c_int32), ("ring_stages", C.c_int32), ("stage_bytes", C.c_int32),
+                ("smem_bytes", C.c_int32), ("ctas_per_sm", C.c_int32), ("tmem_columns", C.c_int32),
+                ("tma_store", C.c_int32), ("stream_k", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+KERNEL_SINGLE, KERNEL_PAIR = 0, 1
+
 EXPORTS = {
     # name: (restype, argtypes)
     "lsnf_abi_version": (C.c_int, []),
@@ -69,6 +78,7 @@ EXPORTS = {
     "lsnf_plan_stage_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StageInfo)]),
     "lsnf_plan_pack_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lsnf_plan_stage_launch_info": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(LaunchInfo)]),
 }
 
 

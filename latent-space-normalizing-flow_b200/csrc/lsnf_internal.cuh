@@ -162,6 +162,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int launch_tapgemm_simt(const StageHost& st, cudaStream_t s);
 int launch_tapgemm_tc(const StageHost& st, cudaStream_t s);
 int tc_encode_maps(lsnf_plan* plan, StageHost& st);
+void tc_launch_info(const StageHost& st, int num_sms, lsnf_launch_info* out);
 int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w, cudaStream_t s);
 int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
 int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);

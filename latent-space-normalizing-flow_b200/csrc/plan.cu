@@ -411,6 +411,14 @@ extern "C" int lsnf_plan_stage_info(const lsnf_plan* plan, int32_t index, lsnf_s
   return LSNF_OK;
 }
 
+extern "C" int lsnf_plan_stage_launch_info(const lsnf_plan* plan, int32_t index, int32_t num_sms,
+                                           lsnf_launch_info* out) {
+  if (!plan || !out || index < 0 || index >= (int)plan->stages.size()) return fail(LSNF_ERR_INVALID, "bad stage index");
+  if (num_sms < 2) return fail(LSNF_ERR_INVALID, "num_sms must be at least 2");
+  tc_launch_info(plan->stages[index], num_sms, out);
+  return LSNF_OK;
+}
+
 static PackGeom geom_of(const StageHost& st) {
   PackGeom g;
   g.kind = st.kind; g.first = st.first; g.last = st.last; g.k = st.k; g.ci = st.ci; g.co = st.co;

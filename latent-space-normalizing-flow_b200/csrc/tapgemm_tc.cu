@@ -989,6 +989,19 @@ static bool tma_store_enabled() {
   return v == 1;
 }
 
+// Which tensor-store map the 16-bit output of a stage gets: 1 stride-2 forward [B][2H][2W][2C], 2 first layer
+// [B][k*k][2C], 3 plain gradient [B][H][W][2C], 4 phase-split gradient; 0 = per-thread stores.
+static int out_tma_kind(const StageHost& sh) {
+  const StageDev& d = sh.dev;
+  const bool wide_single = d.block_n >= 128 && d.n_pad % d.block_n == 0 && d.ksplit == 1;   // 1-CTA kernel, wide N tile
+  if (!(use_pair(sh) || wide_single) || !(d.epi == EPI_ACT_HL || d.epi == EPI_GRAD_HL) || !tma_store_enabled()) return 0;
+  if (d.epi == EPI_ACT_HL && sh.first) return 2;
+  if (d.epi == EPI_ACT_HL && d.ms == 2) return 1;
+  if (d.epi == EPI_GRAD_HL && !d.split) return 3;
+  if (d.epi == EPI_GRAD_HL && d.split && d.bW >= 2 && d.bH >= 2 && (d.bH % 2) == 0) return 4;
+  return 0;
+}
+
 int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return LSNF_ERR_CUDA; }
@@ -1023,33 +1036,33 @@ int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
       return LSNF_ERR_CUDA;
     }
   }
-  // output map of the hi|lo epilogues of the CTA-pair kernel (tensor stores)
+  // output map of the 16-bit epilogues (tensor stores)
   sh.dev.out_tma = 0;
-  const bool wide_single = d.block_n >= 128 && d.n_pad % d.block_n == 0 && d.ksplit == 1;   // 1-CTA kernel, wide N tile
-  if ((use_pair(sh) || wide_single) && (d.epi == EPI_ACT_HL || d.epi == EPI_GRAD_HL) && tma_store_enabled()) {
+  const int want_kind = out_tma_kind(sh);
+  if (want_kind) {
     const cuuint64_t C2 = (cuuint64_t)2 * d.oC, eb = 2;   // channels per position (hi|lo), bytes per element
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
     int kind = 0;
-    if (d.epi == EPI_ACT_HL && sh.first) {                 // [B][k*k][2C]
+    if (want_kind == 2) {                                  // [B][k*k][2C]
       const cuuint64_t kk = (cuuint64_t)sh.k * sh.k;
       dims[0] = C2; dims[1] = kk; dims[2] = 1; dims[3] = 1; dims[4] = d.B;
       strides[0] = C2 * eb; strides[1] = C2 * kk * eb; strides[2] = C2 * kk * eb; strides[3] = C2 * kk * eb;
       box[0] = 64; box[1] = 1; box[2] = 1; box[3] = 1; box[4] = 128;
       kind = 2;
-    } else if (d.epi == EPI_ACT_HL && d.ms == 2) {         // [B][2H][2W][2C] as (c, px, w, py, b*H + h)
+    } else if (want_kind == 1) {                           // [B][2H][2W][2C] as (c, px, w, py, b*H + h)
       const cuuint64_t W = d.Wg, H = d.Hg;
       dims[0] = C2; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (cuuint64_t)d.B * H;
       strides[0] = C2 * eb; strides[1] = 2 * C2 * eb; strides[2] = 2 * W * C2 * eb; strides[3] = 4 * W * C2 * eb;
       box[0] = 64; box[1] = 1; box[2] = d.bW; box[3] = 1; box[4] = d.bB * d.bH;
       kind = 1;
-    } else if (d.epi == EPI_GRAD_HL && !d.split) {         // [B][H][W][2C]
+    } else if (want_kind == 3) {                           // [B][H][W][2C]
       const cuuint64_t W = d.Wg, H = d.Hg;
       dims[0] = C2; dims[1] = W; dims[2] = H; dims[3] = d.B; dims[4] = 1;
       strides[0] = C2 * eb; strides[1] = W * C2 * eb; strides[2] = H * W * C2 * eb; strides[3] = (cuuint64_t)d.B * H * W * C2 * eb;
       box[0] = 64; box[1] = d.bW; box[2] = d.bH; box[3] = d.bB; box[4] = 1;
       kind = 3;
-    } else if (d.epi == EPI_GRAD_HL && d.split && d.bW >= 2 && d.bH >= 2 && (d.bH % 2) == 0) {
+    } else if (want_kind == 4) {
       // [4 = (py,px)][B][H/2][W/2][2C] as (c, w/2, b*(H/2) + h/2, px, py): strides increase monotonically; the
       // epilogue permutes its staging rows accordingly
       const cuuint64_t Wh = d.Wg / 2, Hh = d.Hg / 2;
@@ -1092,6 +1105,22 @@ static int launch_bn(const StageHost& sh, cudaStream_t s) {
   return LSNF_OK;
 }
 
+// Stream-K (equal shares of tiles x K blocks per pair, partial accumulators exchanged through L2) pays only when
+// whole-tile scheduling would leave the pairs badly balanced: it costs a partial-tile round trip per pair.
+// One K block costs about 1 us of tensor time; the partial-tile round trip of stream-K about 35 of them.
+static bool pair_stream_k(const StageDev& st, int max_pairs) {
+  const int mtiles = st.tiles_b * st.tiles_h * st.tiles_w;
+  const int num_tiles = (mtiles + 1) / 2 * (st.n_pad / P_BN) * st.nphase;
+  const int total = st.ph[0].ntaps * (st.Ka / BLOCK_K);
+  const int rounds = (num_tiles + max_pairs - 1) / max_pairs;
+  const long long static_units = (long long)rounds * total;                        // critical path, whole tiles
+  const long long sk_units = ((long long)num_tiles * total + max_pairs - 1) / max_pairs + 35;
+  static int sk_env = -1;
+  if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
+  return (sk_env == 1 || (sk_env == 2 && sk_units < static_units)) && total >= 8 &&
+         (long long)num_tiles * total >= 4LL * max_pairs && max_pairs <= 80;
+}
+
 static int launch_pair(const StageHost& sh, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1109,18 +1138,8 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     max_pairs = sms / 2;
   }
-  // Stream-K (equal shares of tiles x K blocks per pair, partial accumulators exchanged through L2) pays only when
-  // whole-tile scheduling would leave the pairs badly balanced: it costs a partial-tile round trip per pair.
-  const int total = st.ph[0].ntaps * (st.Ka / BLOCK_K);
-  // One K block costs about 1 us of tensor time; the partial-tile round trip of stream-K about 35 of them.
-  const int rounds = (num_tiles + max_pairs - 1) / max_pairs;
-  const long long static_units = (long long)rounds * total;                        // critical path, whole tiles
-  const long long sk_units = ((long long)num_tiles * total + max_pairs - 1) / max_pairs + 35;
-  static int sk_env = -1;
-  if (sk_env < 0) { const char* e = getenv("LSNF_STREAMK"); sk_env = e ? atoi(e) : 2; }   // 0 off, 1 always, 2 auto
   StageDev launch_st = st;
-  launch_st.sk_enable = (sk_env == 1 || (sk_env == 2 && sk_units < static_units)) && total >= 8 &&
-                        (long long)num_tiles * total >= 4LL * max_pairs && max_pairs <= 80;
+  launch_st.sk_enable = pair_stream_k(st, max_pairs);
   const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);
   dim3 grid(2 * pairs, 1, 1);
   if (st.passes == 1)
@@ -1129,6 +1148,40 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
     tapgemm_tc2_kernel<false><<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
+}
+
+// What launch_tapgemm_tc would do for this stage on a device with `num_sms` SMs (no device needed).
+void tc_launch_info(const StageHost& sh_in, int num_sms, lsnf_launch_info* out) {
+  StageHost sh = sh_in;
+  sh.dev.out_tma = out_tma_kind(sh);
+  const StageDev& d = sh.dev;
+  const int mtiles = d.tiles_b * d.tiles_h * d.tiles_w;
+  memset(out, 0, sizeof(*out));
+  out->block = TC_THREADS;
+  out->tma_store = d.out_tma;
+  out->tmem_columns = use_pair(sh) ? 512 : (d.block_n < 32 ? 32 : d.block_n);
+  if (use_pair(sh)) {
+    const int max_pairs = num_sms / 2;
+    const int num_tiles = (mtiles + 1) / 2 * (d.n_pad / P_BN) * d.nphase;
+    out->kernel = LSNF_KERNEL_PAIR;
+    out->stream_k = pair_stream_k(d, max_pairs) ? 1 : 0;
+    out->grid_x = 2 * (out->stream_k ? max_pairs : std::min(num_tiles, max_pairs));
+    out->grid_y = out->grid_z = 1;
+    out->ring_stages = d.passes == 1 ? P_MAX_STAGES : P_STAGES;
+    out->stage_bytes = d.passes == 1 ? P_STAGE_BYTES / 2 : P_STAGE_BYTES;
+    out->smem_bytes = P_SMEM_BYTES;
+    out->ctas_per_sm = 1;
+  } else {
+    const RingGeom g = ring_geometry(d);
+    out->kernel = LSNF_KERNEL_SINGLE;
+    out->grid_x = mtiles; out->grid_y = d.n_pad / d.block_n; out->grid_z = d.nphase * d.ksplit;
+    out->ring_stages = g.nst;
+    out->stage_bytes = (int32_t)g.stage_bytes;
+    out->smem_bytes = (int32_t)g.smem;
+    // shared memory (1 KiB per CTA is reserved by the system), the 2048-thread and 64 Ki-register limits
+    const int by_smem = (TC_SMEM_MAX + 1024) / ((int)g.smem + 1024);
+    out->ctas_per_sm = std::max(1, std::min(by_smem, 2048 / TC_THREADS));
+  }
 }
 
 int launch_tapgemm_tc(const StageHost& sh, cudaStream_t s) {

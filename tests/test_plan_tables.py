@@ -175,3 +175,84 @@ def test_compute_entry_points_fail_loudly_without_binding():
     assert lib.lsnf_workspace_bytes(h) > 0
     assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 3)
     lib.lsnf_plan_destroy(h)
+
+
+# ---- launch geometry of the tcgen05 path (host decisions: which kernel, ring, shared memory, occupancy) --------
+BASELINE_CONFIGS = [("svhn", 100, 64, 100), ("cifar10", 128, 128, 100), ("celeba_crop", 100, 128, 100),
+                    ("celeba_hq256", 128, 64, 8)]
+SMEM_MAX = 232448      # 227 KiB per CTA on sm_100
+SMEM_PER_SM = 233472   # 228 KiB per SM, 1 KiB reserved per resident CTA
+
+
+def launch_infos(lib, h, num_sms=148, bwd_passes=None):
+    out = []
+    for i in range(lib.lsnf_plan_num_stages(h)):
+        li = _cabi.LaunchInfo()
+        _cabi.check(lib.lsnf_plan_stage_launch_info(h, i, num_sms, C.byref(li)), "launch_info")
+        out.append(li)
+    return out
+
+
+@pytest.mark.parametrize("bwd_passes", [1, 3])
+@pytest.mark.parametrize("arch,nz,ngf,batch", BASELINE_CONFIGS)
+def test_launch_geometry_respects_the_hardware_limits(arch, nz, ngf, batch, bwd_passes):
+    lib = _cabi.load()
+    cfg = _cabi.Config(arch=_cabi.ARCH[arch], batch=batch, nz=nz, ngf=ngf, nc=3, f_depth=5, f_width=64,
+                       f_permutation=2, f_coupling=1, leak=0.2, gemm_impl=0, bwd_passes=bwd_passes)
+    h = C.c_void_p()
+    _cabi.check(lib.lsnf_plan_create(C.byref(cfg), C.byref(h)), "create")
+    infos, launches = stage_infos(lib, h), launch_infos(lib, h)
+    for s, li in zip(infos, launches):
+        total = (s.tap_gen_k ** 2 if s.tap_gen_k else s.n_taps[0]) * (s.k_per_tap // 64)   # K blocks per tile
+        assert li.block == 320 and li.grid_x >= 1 and li.grid_y >= 1 and li.grid_z >= 1
+        assert li.smem_bytes <= SMEM_MAX
+        assert li.ring_stages >= 1 and li.ring_stages * li.stage_bytes + 1280 <= li.smem_bytes
+        # the CTAs one SM can hold must fit its shared memory and its 512 TMEM columns
+        assert li.ctas_per_sm >= 1
+        assert li.ctas_per_sm * (li.smem_bytes + 1024) <= SMEM_PER_SM
+        assert li.ctas_per_sm * li.tmem_columns <= 512
+        if li.kernel == _cabi.KERNEL_PAIR:
+            # persistent CTA pairs: 256-wide N tiles, no split-K, a K loop worth pipelining, one pair per SM pair
+            assert s.block_n == 256 and s.n_pad % 256 == 0 and s.k_splits == 1 and total >= 3
+            assert li.grid_x % 2 == 0 and li.grid_x <= 148 and li.ctas_per_sm == 1 and li.tmem_columns == 512
+            assert li.ring_stages * li.stage_bytes == 3 * 65536
+            assert (li.ring_stages == 6) == (s.passes == 1)
+            if li.stream_k:
+                assert li.grid_x == 148 and total >= 8
+        else:
+            assert (li.grid_x, li.grid_y) == (-(-batch * s.grid_h * s.grid_w // 128), s.n_pad // s.block_n)
+            assert li.grid_z == s.n_phases * s.k_splits and not li.stream_k
+            if total <= 2 or (s.k_splits == 1 and total <= 4):
+                assert li.ctas_per_sm >= 2, "short K loops must leave room for a second CTA per SM"
+        if li.tma_store:
+            # 16-bit outputs of wide tiles only, and 32 KiB of staging must exist
+            assert s.epilogue in (0, 2) and s.block_n >= 128 and s.k_splits == 1
+            if li.kernel == _cabi.KERNEL_SINGLE:
+                assert li.ring_stages * li.stage_bytes >= 32768
+    # the headline configuration: both wide forward layers and their data gradients run on the pair kernel
+    if arch == "cifar10":
+        kinds = [li.kernel for li in launches]
+        assert kinds == [0, 1, 1, 0, 0, 1, 1, 0]
+    lib.lsnf_plan_destroy(h)
+
+
+def test_launch_geometry_scales_with_the_sm_count():
+    lib, h = make_plan("cifar10", 128, 128, 100)
+    for sms in (148, 132, 64):
+        for li in launch_infos(lib, h, sms):
+            if li.kernel == _cabi.KERNEL_PAIR:
+                assert li.grid_x <= sms - sms % 2
+    li = _cabi.LaunchInfo()
+    assert lib.lsnf_plan_stage_launch_info(h, 99, 148, C.byref(li)) == -1
+    assert lib.lsnf_plan_stage_launch_info(h, 0, 1, C.byref(li)) == -1
+    lib.lsnf_plan_destroy(h)
+
+
+def test_multiply_high_division_of_the_fused_last_layer_kernel_is_exact():
+    # gen_aux.cu FastDiv: x / d == umulhi(x, floor((2^32 - 1) / d) + 1) whenever x * d < 2^32; the kernel divides
+    # tile-local indices (< 2^16) by tile extents (< 2^11)
+    rng = np.random.default_rng(0)
+    for d in list(range(2, 70)) + [96, 128, 258, 660, 1020, 1980, 2047]:
+        m = (0xFFFFFFFF // d) + 1
+        xs = np.concatenate([np.arange(0, 4096), rng.integers(0, min(2 ** 32 // d, 2 ** 20), 4096)]).astype(np.uint64)
+        assert np.array_equal((xs * np.uint64(m)) >> np.uint64(32), xs // np.uint64(d)), d
