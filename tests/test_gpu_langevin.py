@@ -199,6 +199,30 @@ def test_cifar_full_config_one_step_against_oracle():
     assert abs(gn.item() - gnr.item()) < 1e-3 * gnr.item() and abs(fn.item() - fnr.item()) < 1e-3 * fnr.item()
 
 
+def test_hq256_architecture_two_steps_against_oracle():
+    # the 7-layer 256x256 generator (model.py:117-151): the only shape whose last layer spans several column tiles of
+    # the fused gather / loss-gradient kernel (128 input columns, 32 per tile) and whose deep layers have 1-2 M tiles
+    c = dict(dataset="celeba_hq256", nz=128, ngf=64, B=3, sigma=0.3, T=2)
+    args, netG, netF = build(c, seed=6)
+    x_np, z0_np, eps_np = synth.inputs(3, 128, 3, 256, 2, seed=6)
+    zr, gnr, fnr = refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np),
+                                    to_torch(synth.generator_state("celeba_hq256", 128, 64, seed=6)),
+                                    to_torch(synth.flow_state(128, 64, seed=6)),
+                                    refpath.generator_layers("celeba_hq256", 128, 64),
+                                    depth=5, steps=2, step_size=0.1, sigma=0.3, eps=torch.from_numpy(eps_np))
+    for passes in (1, 3):
+        z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(
+            torch.from_numpy(z0_np).to(DEV), torch.from_numpy(x_np).to(DEV), netG, netF, args,
+            eps=torch.from_numpy(eps_np).to(DEV), bwd_passes=passes)
+        assert rel_l2(z.cpu(), zr) < REL_TOL, passes
+        assert abs(gn.item() - gnr.item()) < 2e-3 * gnr.item() and abs(fn.item() - fnr.item()) < 1e-3 * fnr.item()
+    with torch.no_grad():
+        xh = netG(torch.from_numpy(z0_np).to(DEV))
+    want = refpath.generator_forward(to_torch(synth.generator_state("celeba_hq256", 128, 64, seed=6)),
+                                     torch.from_numpy(z0_np), refpath.generator_layers("celeba_hq256", 128, 64))
+    assert rel_err(xh.cpu(), want) < REL_TOL
+
+
 def test_module_interface_and_checkpoint_keys():
     c = dict(dataset="svhn", nz=100, ngf=32, B=4)
     args, netG, netF = build(c)
