@@ -5,11 +5,15 @@
 //
 // * A rows are 128 grid positions (b, m, n) fetched by ONE 5-D TMA box per tap and K block; the (dy, dx) shift
 //   moves the box, and TMA's out-of-bounds zero fill supplies the convolution padding and the ragged batch.
-// * Operands are 16-bit hi|lo pairs (value = hi + lo; fp16 for the forward pass, bf16 for the data gradients); each
+// * Operands are 16-bit hi|lo pairs (value = hi + lo; fp16 for the forward pass, bf16 for 3-pass data gradients); each
 //   K step issues three tcgen05.mma (lo*hi, hi*lo, hi*hi) into one fp32 TMEM accumulator -- the 3-pass split that
-//   keeps z_T within the 1e-4 parity budget.
+//   keeps z_T within the 1e-4 parity budget.  Single-pass stages (passes == 1: the data gradient of noisy chains)
+//   load and multiply the hi halves only.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
-//   (tcgen05.ld -> bias/activation/derivative -> bf16 hi|lo or fp32 stores).
+//   (tcgen05.ld -> bias / LeakyReLU / LeakyReLU' from bit-packed signs -> 16-bit hi|lo through TMA tensor stores,
+//   or fp32 rows).  Two kernels: tapgemm_tc_kernel<BN> (one CTA per tile, ring sized per launch) and
+//   tapgemm_tc2_kernel<DEEP> (persistent cta_group::2 pairs for the 256-wide stages); the host picks per stage
+//   (use_pair, ring_geometry, out_tma_kind, pair_stream_k -- mirrored by lsnf_plan_stage_launch_info).
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
