@@ -1,5 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
+# A/B of two library builds on the same box: tools/_ab/liblsnf_old.so (tools/build_ab_lib.sh <commit>) against the in-tree build
 timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_gpu_ab.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/t_gpu39.log
 for r in 1 2; do
 for v in old new; do
