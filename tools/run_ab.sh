@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B of two library builds on the same box: tools/_ab/liblsnf_old.so (tools/build_ab_lib.sh <commit>) against the in-tree build
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_gpu_ab.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/t_gpu39.log
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_gpu_ab.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/t_gpu_ab.log
 for r in 1 2; do
 for v in old new; do
   if [ $v = new ]; then unset LSNF_LIB; else export LSNF_LIB=$PWD/tools/_ab/liblsnf_$v.so; fi
