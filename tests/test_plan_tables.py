@@ -178,8 +178,9 @@ def test_compute_entry_points_fail_loudly_without_binding():
 
 
 # ---- launch geometry of the tcgen05 path (host decisions: which kernel, ring, shared memory, occupancy) --------
-BASELINE_CONFIGS = [("svhn", 100, 64, 100), ("cifar10", 128, 128, 100), ("celeba_crop", 100, 128, 100),
-                    ("celeba_hq256", 128, 64, 8)]
+import bench  # noqa: E402  (the BASELINE.json configurations live in bench.WORKLOADS)
+
+BASELINE_CONFIGS = [(w["dataset"], w["nz"], w["ngf"], w["B"]) for w in bench.WORKLOADS.values()]
 SMEM_MAX = 232448      # 227 KiB per CTA on sm_100
 SMEM_PER_SM = 233472   # 228 KiB per SM, 1 KiB reserved per resident CTA
 
