@@ -23,11 +23,9 @@ class AttrDict(dict):
 
 
 def make_args(**overrides) -> AttrDict:
-    """Defaults of train.py:37-99 for every flag the hot path reads; ``overrides`` use the CLI flag names."""
-    a = AttrDict(test_mode=False, seed=1, dataset="svhn", img_size=32, batch_size=100, nz=100, nc=3, ngf=64,
-                 g_llhd_sigma=0.3, g_activation="lrelu", g_activation_leak=0.2, g_l_steps=20, g_l_step_size=0.1,
-                 g_l_with_noise=True, g_batchnorm=False, f_n_levels=1, f_depth=5, f_flow_permutation=2, f_width=64,
-                 f_flow_coupling=1)
+    """Defaults of train.py:37-99 (``cli.FLAGS``); ``overrides`` use the CLI flag names."""
+    from .cli import defaults
+    a = AttrDict(defaults())
     unknown = set(overrides) - set(a) - {"device", "job_id", "status"}
     if unknown:
         raise TypeError(f"unknown argument(s): {sorted(unknown)}")
