@@ -103,3 +103,21 @@ def sample_x(netG: _netG, netF: _netF, n: int, device, generator: Optional[torch
     z, _ = netF.inverse(eps)
     xs = netG.generate(z)
     return ((xs + 1.0) / 2.0).clamp(min=0.0, max=1.0)
+
+
+def reconstruction_error(batches, netG: _netG, netF: _netF, args, generator: Optional[torch.Generator] = None) -> float:
+    """The reconstruction report of test mode (train.py:641-662): for every batch ``x`` [B,nc,H,W] on the GPU,
+    z_0 ~ N(0,I), z_k = test-mode Langevin (``g_l_steps * 20`` noise-free iterations), x_hat = G(z_k); returns the
+    mean over batches of ``mse_sum(x_hat, x) / B / nc / H / W`` (the reference divides by ``3 * img_size**2``)."""
+    sampler = make_sampler(args, test_mode=True)
+    total, n = 0.0, 0
+    for x in batches:
+        z0 = torch.randn(x.shape[0], netG.nz, 1, 1, device=x.device, generator=generator)
+        z_k = sampler(z0, x, netG, netF)[0]
+        x_hat = netG.generate(z_k.reshape(x.shape[0], netG.nz))
+        total += float(((x_hat - x) ** 2).sum().item()) / x.shape[0] / x.shape[1] / x.shape[2] / x.shape[3]
+        n += 1
+    if n == 0:
+        raise ValueError("no batches")
+    return total / n
+

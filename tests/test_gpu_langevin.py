@@ -223,6 +223,26 @@ def test_hq256_architecture_two_steps_against_oracle():
     assert rel_err(xh.cpu(), want) < REL_TOL
 
 
+def test_test_mode_reconstruction_report_against_oracle():
+    # train.py:641-662 with --test_mode: g_l_steps*20 noise-free iterations per batch, then mse_sum / B / 3 / H / W
+    c = dict(dataset="svhn", nz=100, ngf=32, B=6, sigma=0.3, T=1)
+    args, netG, netF = build(c, seed=8)
+    x_np, _, _ = synth.inputs(12, 100, 3, 32, 1, seed=8)
+    xs = [torch.from_numpy(x_np[:6]).to(DEV), torch.from_numpy(x_np[6:]).to(DEV)]
+    got = lsnf_b200.reconstruction_error(xs, netG, netF, args, generator=torch.Generator(DEV).manual_seed(11))
+    gen = torch.Generator(DEV).manual_seed(11)
+    gp, fp = to_torch(synth.generator_state("svhn", 100, 32, seed=8)), to_torch(synth.flow_state(100, 64, seed=8))
+    layers = refpath.generator_layers("svhn", 100, 32)
+    want = 0.0
+    for x in xs:
+        z0 = torch.randn(6, 100, 1, 1, device=DEV, generator=gen).cpu()
+        zk, _, _ = refpath.langevin(z0, x.cpu(), gp, fp, layers, depth=5, steps=20, step_size=0.1, sigma=0.3, eps=None)
+        xh = refpath.generator_forward(gp, zk, layers)
+        want += float(((xh - x.cpu()) ** 2).sum()) / 6 / 3 / 32 / 32
+    want /= 2
+    assert abs(got - want) < 1e-4 * want, (got, want)
+
+
 def test_module_interface_and_checkpoint_keys():
     c = dict(dataset="svhn", nz=100, ngf=32, B=4)
     args, netG, netF = build(c)
