@@ -187,7 +187,9 @@ def run_reference(a, w, rank, out):
     line = {"impl": "reference", "metric": "langevin_latent_steps_per_sec", "value": value, "unit": "latent-steps/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": a.workload, **{k: w[k] for k in ("dataset", "nz", "ngf", "f_width", "T", "B")},
+            "config": {"workload": a.workload, "dataset": w["dataset"], "nz": w["nz"], "ngf": w["ngf"],
+                       "f_width": w["f_width"], "g_l_steps": w["T"], "batch_per_gpu": w["B"],
+                       "g_llhd_sigma": w["sigma"], "noise": "none needed for timing (torch CPU oracle)",
                        "cpu": cpu_model()},
             "cpu_baseline": {"value": value, "unit": "latent-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
