@@ -11,6 +11,7 @@
  *   lsnf_flow_inverse        <- netF(z, objective, reverse=True)          train.py:434, :569; model.py:484-498
  *   lsnf_langevin_update     <- z update + noise + diagnostics            train.py:324-329
  *   lsnf_langevin_run        <- sample_langevin_post_z_with_flow          train.py:307-335, :602-634
+ *   lsnf_sample_prior        <- sample_x(): eps -> F^-1 -> G -> [0,1]     train.py:565-576, :433-437, :472-478
  *   lsnf_pack_*              <- parameters of _netG / _netF               model.py:48-157, :460-498
  *
  * Conventions: every function returns 0 on success and a negative lsnf_status otherwise;
@@ -18,8 +19,10 @@
  * DEVICE pointers to contiguous fp32 data in the reference's own layouts (NCHW images, [B,nz] latents,
  * [C_in,C_out,k,k] ConvTranspose2d weights) unless stated otherwise.  `stream` is a cudaStream_t; all work
  * is enqueued on it and no call synchronises the device.  The caller owns every buffer, including the
- * workspace; inputs are never modified.  A plan is tied to one device and one batch size and is not
- * thread-safe; distinct plans may be used concurrently from distinct threads / streams.
+ * workspace; inputs are never modified.  A plan is tied to one device (the current device of lsnf_plan_bind) and one
+ * batch size and is not thread-safe; distinct plans -- on the same or on different devices of one process -- may be
+ * used concurrently from distinct threads / streams (per-device kernel attributes are set up under a lock at bind
+ * time, nothing on the launch path is process-global).
  *
  * There is no CPU fallback: on a machine without a CUDA device every compute entry point fails with
  * LSNF_ERR_CUDA.
@@ -57,7 +60,9 @@ typedef enum lsnf_arch {
 } lsnf_arch;
 
 typedef enum lsnf_gemm_impl {
-  LSNF_GEMM_TCGEN05 = 0, /* product path: TMA-fed tcgen05 tensor-core tiles, bf16 hi/lo split, 3 passes */
+  LSNF_GEMM_TCGEN05 = 0, /* product path: TMA-fed tcgen05 tensor-core tiles on 16-bit hi|lo operand pairs (value =
+                            hi + lo): fp16 pairs with power-of-two-scaled weights in the forward pass, bf16 pairs in the
+                            data gradient; three MMAs per K step (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM */
   LSNF_GEMM_SIMT = 1     /* debugging twin on CUDA cores over the same buffers (tests only) */
 } lsnf_gemm_impl;
 
@@ -73,9 +78,10 @@ typedef struct lsnf_config {
   int32_t f_coupling;    /* --f_flow_coupling: 1 = affine (default), 0 = additive */
   float leak;            /* --g_activation_leak of the LeakyReLU (0.2) */
   int32_t gemm_impl;     /* lsnf_gemm_impl */
-  int32_t bwd_passes;    /* tensor-core passes of the data-gradient stages: 0 or 3 = hi/lo split, 3 MMAs per K step
-                            (gradient as exact as the forward pass); 1 = single fp16 pass (gradient to ~2e-4,
-                            z_T still within the 1e-4 budget -- DESIGN.md section 4.1) */
+  int32_t bwd_passes;    /* tensor-core passes of the data-gradient stages: 0 or 3 (default) = bf16 hi|lo split, 3 MMAs
+                            per K step: arithmetic not narrower than the reference's fp32.  1 = explicit opt-in to a
+                            single fp16 pass (11-bit significands, gradient good to ~2e-4): a reduced-precision mode,
+                            measured margins in DESIGN.md section 4.1 */
   int32_t reserved[4];
 } lsnf_config;
 
@@ -99,7 +105,8 @@ int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes);
 
 /* ---- parameters ------------------------------------------------------------------------------------- */
 /* weights[i]: [C_in,C_out,k,k], biases[i]: [C_out] of the i-th ConvTranspose2d (gen.{3i}.weight|bias).
- * Re-packs into the bf16 hi/lo K-major operand layouts of every forward and data-gradient stage. */
+ * Re-packs into the 16-bit hi|lo K-major operand layouts of every stage: fp16 pairs times a per-layer power of two for
+ * the forward stages, bf16 pairs for the data-gradient stages (single fp16 halves when bwd_passes == 1). */
 int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* weights, const float* const* biases,
                                 int32_t n_layers, lsnf_stream stream);
 /* params: f_depth * LSNF_FLOW_PTRS_PER_STEP device pointers (order above).  For f_permutation == 1 the
@@ -137,6 +144,11 @@ int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad_g, const f
 int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t steps, float step_size,
                       float sigma, int32_t with_noise, const float* eps, uint64_t seed, uint64_t sample_offset,
                       float* z_out, float* gnorms, lsnf_stream stream);
+/* Prior sampling, train.py:565-576 (also :433-437, :472-478): eps [B,nz] ~ N(0,I) -> z = F^-1(eps) -> x = G(z)
+ * [B,nc,H,W]; with to_unit_range != 0 the store applies to_range_0_1 and the clamp of train.py:573,
+ * x = clamp((G(z) + 1) / 2, 0, 1).  z (nullable) receives the latents [B,nz].  eps is not modified.  Needs flow
+ * weights packed with w_inverse. */
+int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int32_t to_unit_range, lsnf_stream stream);
 /* Launches generator stage `index` alone (0..L-1 forward, L..2L-1 data gradient) on the buffers currently in the
  * workspace.  Profiling / test hook: bench.py times the dominant tap-GEMM with CUDA events through it. */
 int lsnf_plan_run_stage(lsnf_plan* plan, int32_t index, lsnf_stream stream);
@@ -168,7 +180,9 @@ typedef struct lsnf_stage_info {
   int32_t out_off_y[LSNF_MAX_PHASES], out_off_x[LSNF_MAX_PHASES];
   int32_t out_phase_split; /* output written in phase-split layout */
   int32_t out_channels;  /* channels per output position (n_pad may span several positions) */
-  int32_t epilogue;      /* 0 bias+lrelu -> bf16 hi/lo, 1 bias+tanh -> fp32 NCHW, 2 *lrelu' -> bf16 hi/lo, 3 raw fp32 rows (split-K partials / per-tap products of the last forward layer) */
+  int32_t epilogue;      /* 0 bias+lrelu -> fp16 hi|lo + sign bits, 1 bias+tanh -> fp32 NCHW, 2 *lrelu' -> bf16 hi|lo (fp16
+                            hi only when bwd_passes == 1), 3 raw fp32 rows (split-K partials / per-tap products of the
+                            last forward layer) */
   int32_t k_splits;
   int32_t a_planes;      /* planes of the A operand (4 when phase-split) */
   int32_t a_h, a_w;      /* spatial extent of the A operand (== grid except for the first layer's data gradient) */

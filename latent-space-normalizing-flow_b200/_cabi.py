@@ -72,6 +72,7 @@ EXPORTS = {
                                        C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "lsnf_langevin_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsnf_sample_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "lsnf_plan_run_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "lsnf_langevin_launch_count": (C.c_int, [C.c_void_p, C.c_int32]),
     "lsnf_plan_num_stages": (C.c_int, [C.c_void_p]),

@@ -4,6 +4,8 @@
 // (revnet2d_step), :280-294 (actnorm), :179-198 (invertible_1x1_conv), :306-350 (coupling MLP),
 // train.py:316-323 (log-prior and its gradient).  Backward formulas: SURVEY.md section 8a, row A5
 // (pinned against autograd in fp64 by tests/test_oracle_golden.py).
+#include <mutex>
+
 #include "lsnf_internal.cuh"
 
 namespace lsnf {
@@ -601,24 +603,34 @@ static int flow_ring_floats(const FlowLayout& f, size_t fixed, int depth, bool b
 
 template <int S>
 static int launch_fwd_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
-  static size_t cur = 0;   // raised lazily, outside any stream capture (the first call of a plan is eager)
-  if (smem > cur) {
-    LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cur = smem;
-  }
   flow_forward_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
 template <int S>
 static int launch_inv_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
-  static size_t cur = 0;
-  if (smem > cur) {
-    LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cur = smem;
-  }
   flow_inverse_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
   LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+// opt-in shared-memory limit of every instantiation, once per device (lsnf_plan_bind)
+int flow_prepare_device(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) { set_error("device index out of range"); return LSNF_ERR_INVALID; }
+  if (done[device]) return LSNF_OK;
+  const int lim = 227 * 1024;
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  done[device] = true;
   return LSNF_OK;
 }
 

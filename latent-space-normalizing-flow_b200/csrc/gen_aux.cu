@@ -1,5 +1,7 @@
 // Small HBM-bound kernels around the generator tap-GEMMs: weight packing, latent splitting, the
 // reconstruction-gradient seed (with its im2col), split-K reduction and the fused Langevin update.
+#include <mutex>
+
 #include "lsnf_internal.cuh"
 
 namespace lsnf {
@@ -104,7 +106,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256) last_gather_tanh_kernel(const float* __restrict__ d,
                                                                const float* __restrict__ bias,
                                                                float* __restrict__ xhat, int B, int nc, int img,
-                                                               int hin, int p, int n_pad) {
+                                                               int hin, int p, int n_pad, int to_unit_range) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * nc * img * img;
   if (i >= total) return;
@@ -127,22 +129,24 @@ __global__ void __launch_bounds__(256) last_gather_tanh_kernel(const float* __re
   float acc = bias[c];
 #pragma unroll
   for (int t = 0; t < T * T; ++t) acc += v[t];
-  xhat[i] = tanhf(acc);
+  const float t = tanhf(acc);
+  // prior sampling (train.py:562, :573): to_range_0_1(x).clamp(0, 1) fused into the same store
+  xhat[i] = to_unit_range ? fminf(fmaxf((t + 1.f) / 2.f, 0.f), 1.f) : t;
 }
 
-int launch_last_gather(const lsnf_plan* plan, cudaStream_t s) {
+int launch_last_gather(const lsnf_plan* plan, float* out, int to_unit_range, cudaStream_t s) {
   const auto& y = plan->layers[plan->n_layers - 1];
   const long long total = (long long)plan->cfg.batch * plan->cfg.nc * plan->img * plan->img;
   const float* d = (const float*)(plan->ws + plan->off_dlast);
   const float* bias = (const float*)(plan->ws + plan->off_bias[plan->n_layers - 1]);
-  float* xh = (float*)(plan->ws + plan->off_xhat);
+  float* xh = out ? out : (float*)(plan->ws + plan->off_xhat);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (y.k == 3 && y.s == 1)
     last_gather_tanh_kernel<3, 1><<<blocks, 256, 0, s>>>(d, bias, xh, plan->cfg.batch, plan->cfg.nc, plan->img, y.hin,
-                                                        y.p, plan->dlast_pad);
+                                                        y.p, plan->dlast_pad, to_unit_range);
   else
     last_gather_tanh_kernel<4, 2><<<blocks, 256, 0, s>>>(d, bias, xh, plan->cfg.batch, plan->cfg.nc, plan->img, y.hin,
-                                                        y.p, plan->dlast_pad);
+                                                        y.p, plan->dlast_pad, to_unit_range);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -172,6 +176,8 @@ int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 // seed of the reconstruction gradient (train.py:313-314):
 //   g[b,c,oy,ox] = (x_hat - x) / sigma^2 * (1 - x_hat^2)          (MSE-sum derivative times tanh')
+// of which only seed_scale = sigma_seed_scale(sigma) <= 16 (a power of two) is applied here; the rest of 1/sigma^2
+// multiplies the fp32 sum of the first layer's split-K partials (langevin_update_kernel / reduce_partial_kernel),
 // written directly as the im2col operand of the last layer's data gradient:
 //   A[b][iy][ix][tap*nc + c] = g[b][c][iy*s - p + ky][ix*s - p + kx]  (0 outside the image), 64 columns.
 // ---------------------------------------------------------------------------------------------------
@@ -182,7 +188,7 @@ constexpr int IM2COL_SEG = 32;
 __global__ void __launch_bounds__(128) recon_grad_im2col_kernel(const float* __restrict__ xhat,
                                                                 const float* __restrict__ x,
                                                                 uint16_t* __restrict__ a, int B, int nc, int img,
-                                                                int hin, int k, int s, int p, float inv_sigma2,
+                                                                int hin, int k, int s, int p, float seed_scale,
                                                                 int fp16) {
   extern __shared__ float g[];   // [nc][k][span], span = (seg-1)*s + k
   const int segs = (hin + IM2COL_SEG - 1) / IM2COL_SEG;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(128) recon_grad_im2col_kernel(const float* __r
     if (oy >= 0 && oy < img && ox >= 0 && ox < img) {
       const size_t o = (((size_t)b * nc + c) * img + oy) * img + ox;
       const float xh = xhat[o];
-      v = (xh - x[o]) * inv_sigma2 * (1.f - xh * xh);
+      v = (xh - x[o]) * seed_scale * (1.f - xh * xh);
     }
     g[i] = v;
   }
@@ -224,7 +230,7 @@ int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma,
   const size_t smem = (size_t)plan->cfg.nc * y.k * span * 4;
   recon_grad_im2col_kernel<<<plan->cfg.batch * y.hin * segs, 128, smem, s>>>(
       (const float*)(plan->ws + plan->off_xhat), x, (uint16_t*)(plan->ws + plan->off_im2col), plan->cfg.batch,
-      plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p, 1.f / (sigma * sigma), plan->cfg.bwd_passes == 1 ? 1 : 0);
+      plan->cfg.nc, plan->img, y.hin, y.k, y.s, y.p, sigma_seed_scale(sigma), plan->cfg.bwd_passes == 1 ? 1 : 0);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -250,7 +256,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256) last_fused_kernel(const float* __restrict__ d, const float* __restrict__ bias,
                                                          const float* __restrict__ x, float* __restrict__ xhat,
                                                          uint16_t* __restrict__ a, int B, int nc, int img, int hin,
-                                                         int p, int n_pad, int TR, int TC, float inv_sigma2, int fp16,
+                                                         int p, int n_pad, int TR, int TC, float seed_scale, int fp16,
                                                          int write_lo) {
   extern __shared__ float fs[];
   constexpr int T = (K + S - 1) / S;
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(256) last_fused_kernel(const float* __restrict
       const int iyo = oy / S, ixo = ox / S;   // the tile that owns this pixel writes x_hat
       if (iyo >= r0 && iyo < r0 + nr && ixo >= c0 && ixo < c0 + ncol)
         xhat[(((size_t)b * nc + c) * img + oy) * img + ox] = xh;
-      g = (xh - G[i]) * inv_sigma2 * (1.f - xh * xh);
+      g = (xh - G[i]) * seed_scale * (1.f - xh * xh);
     }
     G[i] = g;
   }
@@ -386,21 +392,15 @@ int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaSt
   float* xh = (float*)(plan->ws + plan->off_xhat);
   uint16_t* a = (uint16_t*)(plan->ws + plan->off_im2col);
   const int one = plan->cfg.bwd_passes == 1 ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
   if (smem > 160 * 1024) { set_error("fused last-layer kernel: tile does not fit shared memory"); return LSNF_ERR_INVALID; }
   if (y.k == 3 && y.s == 1)
     last_fused_kernel<3, 1><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
                                                                       plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      1.f / (sigma * sigma), one, !one);
+                                                                      sigma_seed_scale(sigma), one, !one);
   else
     last_fused_kernel<4, 2><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
                                                                       plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      1.f / (sigma * sigma), one, !one);
+                                                                      sigma_seed_scale(sigma), one, !one);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -410,19 +410,19 @@ int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaSt
 // folds this sum into the update kernel)
 // ---------------------------------------------------------------------------------------------------
 __global__ void reduce_partial_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int B, int nz,
-                                      int nzp) {
+                                      int nzp, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * nz) return;
   const int b = i / nz, j = i % nz;
   float acc = 0.f;
   for (int s = 0; s < S; ++s) acc += part[((size_t)s * B + b) * nzp + j];
-  g[i] = acc;
+  g[i] = acc * scale;
 }
 
-int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s) {
+int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, float scale, cudaStream_t s) {
   const int n = plan->cfg.batch * plan->cfg.nz;
   reduce_partial_kernel<<<(n + 255) / 256, 256, 0, s>>>((const float*)(plan->ws + plan->off_partial), grad_z,
-                                                       plan->ksplit_first, plan->cfg.batch, plan->cfg.nz, plan->nzp);
+                                                       plan->ksplit_first, plan->cfg.batch, plan->cfg.nz, plan->nzp, scale);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -459,12 +459,12 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 // split-K partial sums of the reconstruction gradient (fixed summation order -> deterministic).
 __global__ void __launch_bounds__(256) langevin_update_kernel(
     float* __restrict__ z, const float* __restrict__ gg, const float* __restrict__ partial, int nsplit, int nzp,
-    const float* __restrict__ gf, const float* __restrict__ eps, uint16_t* __restrict__ zhl, int B, int nz,
+    float gscale, const float* __restrict__ gf, const float* __restrict__ eps, uint16_t* __restrict__ zhl, int B, int nz,
     int kp, float step, int with_noise, uint64_t seed, uint64_t sample_offset, uint32_t step_idx,
     const uint64_t* __restrict__ dyn, float* __restrict__ norm_scratch, unsigned int* __restrict__ ticket,
     float* __restrict__ gnorms) {
   __shared__ float4 part[8][64];
-  if (dyn) { seed = dyn[0]; sample_offset = dyn[1]; }   // per-call values of a replayed CUDA graph
+  if (dyn) { seed = dyn[0]; sample_offset = dyn[1]; step_idx += (uint32_t)dyn[2]; }   // per-call values of a replayed CUDA graph
   __shared__ float red[2][256];
   __shared__ bool is_last;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(256) langevin_update_kernel(
       const float4 p = part[k][q];
       g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
     }
+    g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;   // the part of 1/sigma^2 kept out of the 16-bit tensors
     const size_t o = (size_t)b * nz + 4 * q;
     const float4 f = *reinterpret_cast<const float4*>(gf + o);
     float4 v = *reinterpret_cast<const float4*>(z + o);
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(256) langevin_update_kernel(
   }
 }
 
-int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit,
+int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit, float gscale,
                   const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
                   uint64_t sample_offset, uint32_t step_idx, const uint64_t* dyn, float* gnorms, int write_zhl,
                   cudaStream_t s) {
@@ -568,20 +569,32 @@ int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float*
   unsigned int* ticket = (unsigned int*)(plan->ws + plan->off_scalars);  // last-block-done counter
   float* scratch = (float*)(plan->ws + plan->off_norms);
   uint16_t* zhl = (write_zhl && plan->n_layers) ? (uint16_t*)(plan->ws + plan->off_zhl) : nullptr;
-  langevin_update_kernel<<<B, 256, 0, s>>>(z, gg, partial, nsplit, plan->nzp, gf, eps, zhl, B, plan->cfg.nz,
+  langevin_update_kernel<<<B, 256, 0, s>>>(z, gg, partial, nsplit, plan->nzp, gscale, gf, eps, zhl, B, plan->cfg.nz,
                                            plan->kp, step, with_noise, seed, sample_offset, step_idx, dyn, scratch,
                                            ticket, gnorms);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
 
-__global__ void set_dyn_kernel(uint64_t* dyn, uint64_t seed, uint64_t sample_offset) {
-  dyn[0] = seed; dyn[1] = sample_offset;
+__global__ void set_dyn_kernel(uint64_t* dyn, uint64_t seed, uint64_t sample_offset, uint64_t base_step) {
+  dyn[0] = seed; dyn[1] = sample_offset; dyn[2] = base_step;
 }
 
-int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, cudaStream_t s) {
-  set_dyn_kernel<<<1, 1, 0, s>>>((uint64_t*)(plan->ws + plan->off_dyn), seed, sample_offset);
+int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, uint32_t base_step, cudaStream_t s) {
+  set_dyn_kernel<<<1, 1, 0, s>>>((uint64_t*)(plan->ws + plan->off_dyn), seed, sample_offset, base_step);
   LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
+int aux_prepare_device(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) { set_error("device index out of range"); return LSNF_ERR_INVALID; }
+  if (done[device]) return LSNF_OK;
+  LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  LSNF_CUDA(cudaFuncSetAttribute(last_fused_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  done[device] = true;
   return LSNF_OK;
 }
 

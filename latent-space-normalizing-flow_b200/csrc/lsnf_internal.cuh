@@ -80,6 +80,7 @@ struct StageHost {
   size_t a_off = 0, b_off = 0, out_off = 0, mbits_off = 0, bias_off = 0;
   size_t b_bytes = 0;
   bool last = false, first = false;
+  int num_sms = 148;   // SM count of the plan's device (set by lsnf_plan_bind): persistent grids, stream-K shares
 };
 
 struct FlowLayout {
@@ -120,12 +121,15 @@ struct lsnf_plan {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // CUDA graphs of the whole g_l_steps loop, keyed by (steps, step_size, sigma, with_noise); per-call values
   // (seed, sample offset) are read from device memory, inputs are staged into the workspace
+  // A graph holds one CHUNK of at most `graph_chunk` iterations; the step index of its first iteration is read
+  // from device memory (dyn[2]), so a chain of any length replays the same few graphs (train.py:606: 8 000 steps).
   struct LoopGraph { int steps; float step_size, sigma; int with_noise; cudaGraphExec_t exec; };
   std::vector<LoopGraph> graphs;
   cudaStream_t cap_stream = nullptr;
   size_t off_x = 0, off_gnorms = 0, off_dyn = 0, off_sk_slots = 0, off_sk_flags = 0;
   long long runs = 0;
   bool use_graphs = true;
+  int graph_chunk = 40;
 };
 
 namespace lsnf {
@@ -166,21 +170,37 @@ void tc_launch_info(const StageHost& st, int num_sms, lsnf_launch_info* out);
 int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w, cudaStream_t s);
 int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
 int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);
-int launch_last_gather(const lsnf_plan* plan, cudaStream_t s);
+int launch_last_gather(const lsnf_plan* plan, float* out, int to_unit_range, cudaStream_t s);
 int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
 int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
-int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, cudaStream_t s);
+int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, float scale, cudaStream_t s);
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                      const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,
                      cudaStream_t s);
 int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
                         float* grad_z, cudaStream_t s);
 int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s);
-int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit,
+int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit, float gscale,
                   const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
                   uint64_t sample_offset, uint32_t step_idx, const uint64_t* dyn, float* gnorms,
                   int write_zhl, cudaStream_t s);
-int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, cudaStream_t s);
+int launch_set_dyn(const lsnf_plan* plan, uint64_t seed, uint64_t sample_offset, uint32_t base_step, cudaStream_t s);
+// Per-device one-time setup (opt-in shared-memory limits of every kernel instantiation).  Called by
+// lsnf_plan_bind for the plan's device; thread-safe; nothing on the launch path touches function attributes.
+int tc_prepare_device(int device);
+int aux_prepare_device(int device);
+int flow_prepare_device(int device);
+
+// The loss-gradient seed (x_hat - x) / sigma^2 * (1 - x_hat^2) carries 1/sigma^2 (train.py:313).  Only a power of
+// two of at most 16 of it is baked into the 16-bit gradient tensors (so a small --g_llhd_sigma cannot overflow
+// them); the remaining factor is applied in fp32 where the first layer's split-K partials are summed.
+inline float sigma_seed_scale(float sigma) {
+  const float inv = 1.f / (sigma * sigma);
+  float s = 1.f;
+  while (s * 2.f <= inv && s < 16.f) s *= 2.f;
+  return s;
+}
+inline float sigma_post_scale(float sigma) { return 1.f / (sigma * sigma) / sigma_seed_scale(sigma); }
 
 // (row, col) of W[ci][co][ky][kx] in the packed B operand of a stage; shared by host and device
 struct PackGeom {

@@ -451,8 +451,13 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
   plan->device = dev;
   plan->num_sms = prop.multiProcessorCount;
   plan->ws = (char*)workspace;
+  {
+    int rc;
+    if ((rc = tc_prepare_device(dev)) || (rc = aux_prepare_device(dev)) || (rc = flow_prepare_device(dev))) return rc;
+  }
   for (auto& st : plan->stages) {
     StageDev& d = st.dev;
+    st.num_sms = plan->num_sms;
     d.a = (const __nv_bfloat16*)(plan->ws + st.a_off);
     d.b = (const __nv_bfloat16*)(plan->ws + st.b_off);
     d.out = plan->ws + st.out_off;
@@ -478,6 +483,8 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
   {
     const char* e = getenv("LSNF_NO_GRAPH");
     plan->use_graphs = !(e && e[0] == '1');
+    const char* c = getenv("LSNF_GRAPH_CHUNK");
+    if (c && atoi(c) > 0) plan->graph_chunk = atoi(c);
   }
   plan->bound = true;
   plan->g_packed = plan->f_packed = false;
@@ -535,7 +542,7 @@ static int gen_forward(lsnf_plan* p, const float* z, float* x_hat, cudaStream_t 
   if (split && (rc = launch_split_z(p, z, s))) return rc;
   for (int l = 0; l < p->n_layers; ++l)
     if ((rc = run_stage(p, p->stages[l], s))) return rc;
-  if ((rc = launch_last_gather(p, s))) return rc;
+  if ((rc = launch_last_gather(p, nullptr, 0, s))) return rc;
   if (x_hat) {
     const size_t bytes = (size_t)p->cfg.batch * p->cfg.nc * p->img * p->img * 4;
     LSNF_CUDA(cudaMemcpyAsync(x_hat, p->ws + p->off_xhat, bytes, cudaMemcpyDeviceToDevice, s));
@@ -571,7 +578,7 @@ extern "C" int lsnf_generator_dgrad(lsnf_plan* plan, const float* x, float sigma
   if (!x || !grad_z || !(sigma > 0.f)) return fail(LSNF_ERR_INVALID, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = gen_dgrad_partial(plan, x, sigma, s))) return rc;
-  return launch_reduce_partial(plan, grad_z, s);
+  return launch_reduce_partial(plan, grad_z, sigma_post_scale(sigma), s);
 }
 
 extern "C" int lsnf_flow_forward(lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
@@ -590,19 +597,38 @@ extern "C" int lsnf_flow_inverse(lsnf_plan* plan, const float* eps, float* z, fl
   return launch_flow_inverse(plan, eps, z, neg_objective, (cudaStream_t)stream);
 }
 
+extern "C" int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int32_t to_unit_range,
+                                 lsnf_stream stream) {
+  int rc = need(plan, true, true);
+  if (rc) return rc;
+  if (!eps || !x) return fail(LSNF_ERR_INVALID, "null argument");
+  if (!plan->have_winv) return fail(LSNF_ERR_STATE, "flow weights were packed without w_inverse");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* zw = (float*)(plan->ws + plan->off_z);
+  if ((rc = launch_flow_inverse(plan, eps, zw, nullptr, s))) return rc;          // train.py:568-569
+  if ((rc = launch_split_z(plan, zw, s))) return rc;
+  for (int l = 0; l < plan->n_layers; ++l)                                        // train.py:572
+    if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
+  if ((rc = launch_last_gather(plan, x, to_unit_range, s))) return rc;            // train.py:573 fused into the store
+  if (z) LSNF_CUDA(cudaMemcpyAsync(z, zw, (size_t)plan->cfg.batch * plan->cfg.nz * 4, cudaMemcpyDeviceToDevice, s));
+  return LSNF_OK;
+}
+
 extern "C" int lsnf_langevin_update(lsnf_plan* plan, float* z, const float* grad_g, const float* grad_f,
                                     float step_size, const float* eps, int32_t with_noise, uint64_t seed,
                                     uint64_t sample_offset, uint32_t step, float* gnorms, lsnf_stream stream) {
   if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
   if (!z || !grad_g || !grad_f) return fail(LSNF_ERR_INVALID, "null argument");
-  return launch_update(plan, z, grad_g, nullptr, 0, grad_f, step_size, eps, with_noise, seed, sample_offset, step,
+  return launch_update(plan, z, grad_g, nullptr, 0, 1.f, grad_f, step_size, eps, with_noise, seed, sample_offset, step,
                        nullptr, gnorms, 0, (cudaStream_t)stream);
 }
 
 extern "C" int lsnf_langevin_launch_count(const lsnf_plan* plan, int32_t steps) {
   if (!plan) return 0;
-  // per step: L forward + fused gather/tanh/seed/im2col + L data-gradient + flow + update; once: split_z
-  return 1 + steps * (2 * plan->n_layers + 3);
+  // per step: L forward + fused gather/tanh/seed/im2col + L data-gradient + flow + update; once: split_z; per
+  // replayed graph chunk: the kernel that sets (seed, sample offset, first step index) in device memory
+  const int chunks = steps > 0 ? (steps + plan->graph_chunk - 1) / plan->graph_chunk : 0;
+  return 1 + steps * (2 * plan->n_layers + 3) + chunks;
 }
 
 // the g_l_steps loop on stream s: inputs are the workspace copies of z and x
@@ -640,6 +666,7 @@ struct LoopTrace {
 static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_size, float sigma, int with_noise,
                          const float* eps, uint64_t seed, uint64_t sample_offset, const uint64_t* dyn, float* gnorms,
                          cudaStream_t s) {
+  const float gscale = sigma_post_scale(sigma);
   int rc;
   static int trace_env = -1;
   if (trace_env < 0) { const char* e = getenv("LSNF_TRACE"); trace_env = (e && e[0] == '1') ? 1 : 0; }
@@ -676,7 +703,7 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
     LSNF_CUDA(cudaStreamWaitEvent(s, plan->ev_join, 0));
     tr.mark("join flow prior");
     const float* e = eps ? eps + (size_t)t * c.batch * c.nz : nullptr;
-    if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gf, step_size, e, with_noise, seed,
+    if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gscale, gf, step_size, e, with_noise, seed,
                             sample_offset, (uint32_t)t, dyn, t == steps - 1 ? gnorms : nullptr, 1, s)))
       return rc;
     tr.mark("update");
@@ -706,29 +733,36 @@ extern "C" int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* 
     if ((rc = langevin_loop(plan, x, steps, step_size, sigma, with_noise, eps, seed, sample_offset, nullptr, gnorms, s)))
       return rc;
   } else {
+    // The chain is replayed in chunks of at most `graph_chunk` iterations: one graph per chunk length, the index of
+    // a chunk's first iteration (Philox counter) is read from device memory, so test mode's 8 000-step chains
+    // (train.py:606) reuse one 40-iteration graph 200 times instead of instantiating 88 000 kernel nodes.
     float* x_ws = (float*)(plan->ws + plan->off_x);
     float* gn_ws = (float*)(plan->ws + plan->off_gnorms);
     const uint64_t* dyn = (const uint64_t*)(plan->ws + plan->off_dyn);
-    cudaGraphExec_t exec = nullptr;
-    for (auto& g : plan->graphs)
-      if (g.steps == steps && g.step_size == step_size && g.sigma == sigma && g.with_noise == with_noise) exec = g.exec;
-    if (!exec) {
-      cudaGraph_t graph = nullptr;
-      cudaStream_t cs = plan->cap_stream;
-      LSNF_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      rc = langevin_loop(plan, x_ws, steps, step_size, sigma, with_noise, nullptr, 0, 0, dyn, gn_ws, cs);
-      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
-      ce = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
-      if (plan->graphs.size() >= 8) { cudaGraphExecDestroy(plan->graphs.front().exec); plan->graphs.erase(plan->graphs.begin()); }
-      plan->graphs.push_back({steps, step_size, sigma, with_noise, exec});
-    }
     LSNF_CUDA(cudaMemcpyAsync(x_ws, x, (size_t)c.batch * c.nc * plan->img * plan->img * 4, cudaMemcpyDeviceToDevice, s));
-    if ((rc = launch_set_dyn(plan, seed, sample_offset, s))) return rc;
-    LSNF_CUDA(cudaGraphLaunch(exec, s));
+    for (int done = 0; done < steps;) {
+      const int n = std::min(steps - done, plan->graph_chunk);
+      cudaGraphExec_t exec = nullptr;
+      for (auto& g : plan->graphs)
+        if (g.steps == n && g.step_size == step_size && g.sigma == sigma && g.with_noise == with_noise) exec = g.exec;
+      if (!exec) {
+        cudaGraph_t graph = nullptr;
+        cudaStream_t cs = plan->cap_stream;
+        LSNF_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = langevin_loop(plan, x_ws, n, step_size, sigma, with_noise, nullptr, 0, 0, dyn, gn_ws, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+        if (plan->graphs.size() >= 8) { cudaGraphExecDestroy(plan->graphs.front().exec); plan->graphs.erase(plan->graphs.begin()); }
+        plan->graphs.push_back({n, step_size, sigma, with_noise, exec});
+      }
+      if ((rc = launch_set_dyn(plan, seed, sample_offset, (uint32_t)done, s))) return rc;
+      LSNF_CUDA(cudaGraphLaunch(exec, s));
+      done += n;
+    }
     if (gnorms) LSNF_CUDA(cudaMemcpyAsync(gnorms, gn_ws, 8, cudaMemcpyDeviceToDevice, s));
   }
   LSNF_CUDA(cudaMemcpyAsync(z_out, z, zbytes, cudaMemcpyDeviceToDevice, s));

@@ -16,6 +16,7 @@
 //   (use_pair, ring_geometry, out_tma_kind, pair_stream_k -- mirrored by lsnf_plan_stage_launch_info).
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "tapgemm_common.cuh"
@@ -1095,11 +1096,6 @@ int tc_encode_maps(lsnf_plan* plan, StageHost& sh) {
 
 template <int BN>
 static int launch_bn(const StageHost& sh, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
-    attr_set = true;
-  }
   StageDev st = sh.dev;
   const RingGeom g = ring_geometry(st);
   st.nst = g.nst;
@@ -1126,22 +1122,10 @@ static bool pair_stream_k(const StageDev& st, int max_pairs) {
 }
 
 static int launch_pair(const StageHost& sh, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    attr_set = true;
-  }
   const StageDev& st = sh.dev;
   const int mtiles = st.tiles_b * st.tiles_h * st.tiles_w;
   const int num_tiles = (mtiles + 1) / 2 * (st.n_pad / P_BN) * st.nphase;   // an odd tail pairs with an empty tile
-  static int max_pairs = 0;
-  if (!max_pairs) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    max_pairs = sms / 2;
-  }
+  const int max_pairs = sh.num_sms / 2;   // of the plan's device (lsnf_plan_bind)
   StageDev launch_st = st;
   launch_st.sk_enable = pair_stream_k(st, max_pairs);
   const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);
@@ -1186,6 +1170,25 @@ void tc_launch_info(const StageHost& sh_in, int num_sms, lsnf_launch_info* out) 
     const int by_smem = (TC_SMEM_MAX + 1024) / ((int)g.smem + 1024);
     out->ctas_per_sm = std::max(1, std::min(by_smem, 2048 / TC_THREADS));
   }
+}
+
+// opt-in shared-memory limit of every instantiation, once per device (lsnf_plan_bind); function attributes are per
+// device, so a process that drives several GPUs prepares each of them
+int tc_prepare_device(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) { set_error("device index out of range"); return LSNF_ERR_INVALID; }
+  if (done[device]) return LSNF_OK;
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+  LSNF_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+  done[device] = true;
+  return LSNF_OK;
 }
 
 int launch_tapgemm_tc(const StageHost& sh, cudaStream_t s) {

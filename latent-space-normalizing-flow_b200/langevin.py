@@ -47,10 +47,11 @@ def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbo
 
     ``args`` supplies g_l_steps, g_l_step_size, g_l_with_noise, g_llhd_sigma (train.py:311-326).  ``eps``
     [steps,B,nz,1,1] injects the noise (parity runs); otherwise noise is drawn in-kernel from Philox keyed by
-    (seed, sample_offset + b, step), so a sharded batch reproduces the unsharded result bit for bit.  The
+    (seed, sample_offset + b, step), so a sharded batch draws exactly the noise of the unsharded one (the latents
+    then agree up to fp32 summation order: split-K / stream-K cut points depend on the tile count).  The
     diagnostics use the real batch size (the reference's ``view(args.batch_size, -1)`` breaks on a ragged batch).
-    ``bwd_passes``: tensor-core passes of the reconstruction-gradient GEMMs (``plan.default_bwd_passes``): 1 for
-    chains with noise, 3 for noise-free chains, unless given.
+    ``bwd_passes``: tensor-core passes of the reconstruction-gradient GEMMs: 3 (fp32-equivalent hi|lo split) unless
+    the caller opts in to the single fp16 pass with 1 (``plan.default_bwd_passes``).
     """
     if not isinstance(netG, _netG) or not isinstance(netF, _netF):
         raise TypeError("netG / netF must be lsnf_b200._netG / _netF instances")
@@ -97,12 +98,20 @@ def make_sampler(args, test_mode: bool = False):
     return sampler
 
 
-def sample_x(netG: _netG, netF: _netF, n: int, device, generator: Optional[torch.Generator] = None):
-    """Prior sampling of train.py:567-576: eps ~ N(0,I) -> z = F^-1(eps) -> x = G(z), mapped to [0,1]."""
-    eps = torch.randn(n, netG.nz, device=device, generator=generator)
-    z, _ = netF.inverse(eps)
-    xs = netG.generate(z)
-    return ((xs + 1.0) / 2.0).clamp(min=0.0, max=1.0)
+def sample_x(netG: _netG, netF: _netF, n: int, device, generator: Optional[torch.Generator] = None,
+             eps: Optional[torch.Tensor] = None, to_unit_range: bool = True):
+    """Prior sampling of train.py:565-576 as ONE call into the library (``lsnf_sample_prior``): eps ~ N(0,I) ->
+    z = F^-1(eps) -> x = G(z) -> clamp((x + 1) / 2, 0, 1) applied in the store of the last generator kernel.
+    ``eps`` [n,nz] may be supplied (parity runs); otherwise it is drawn from ``generator``."""
+    if eps is None:
+        eps = torch.randn(n, netG.nz, device=device, generator=generator)
+    eps = eps.detach().reshape(n, netG.nz).contiguous().float()
+    if netF.nz != netG.nz:
+        raise ValueError("netG and netF disagree on nz")
+    plan = langevin_plan(netG, netF, n, eps.device, default_bwd_passes())
+    plan.ensure_generator(netG)
+    plan.ensure_flow(netF, need_inverse=True)
+    return plan.sample_prior(eps, to_unit_range=to_unit_range)
 
 
 def reconstruction_error(batches, netG: _netG, netF: _netF, args, generator: Optional[torch.Generator] = None) -> float:

@@ -3,11 +3,12 @@
 error behaviour, so reference checkpoints load and reference call sites keep working.
 
 Execution:
-  * Inference calls (autograd not recording: ``torch.no_grad()``, ``.eval()`` mode, or nothing requiring grad) run the
-    hand-written CUDA kernels through the C ABI.  Non-CUDA tensors are rejected -- there is no CPU fallback.
-  * When autograd IS recording in training mode (the generator / flow parameter updates of train.py:390-415,
-    which SURVEY.md section 8 leaves in torch autograd) the same maths run as ordinary differentiable torch ops.
-    That branch is not part of the Langevin path; ``sample_langevin_post_z_with_flow`` never takes it.
+  * Inference calls (autograd not recording: ``torch.no_grad()``, or ``.eval()`` mode with no input requiring grad)
+    run the hand-written CUDA kernels through the C ABI.  Non-CUDA tensors are rejected -- there is no CPU fallback.
+  * When autograd IS recording (an input requires grad, or training mode with trainable parameters) the same maths
+    run as ordinary differentiable torch ops, so code written against the reference modules (including its own
+    autograd-based Langevin closure) keeps working.  That branch is not part of the Langevin path:
+    ``sample_langevin_post_z_with_flow`` and ``train.training_iteration`` never take it.
 """
 from __future__ import annotations
 
@@ -37,10 +38,14 @@ def _get(args, name, default=None):
 
 
 def _autograd_needed(module: nn.Module, *tensors) -> bool:
-    if not torch.is_grad_enabled() or not module.training:
+    """True when the call has to record an autograd graph: grad mode is on and either an input requires grad (in any
+    module mode -- the reference's own Langevin closures differentiate w.r.t. z in eval mode, train.py:565, :602-634)
+    or the module is in training mode with trainable parameters (the parameter updates of train.py:390-415)."""
+    if not torch.is_grad_enabled():
         return False
-    return any(t.requires_grad for t in tensors if isinstance(t, torch.Tensor)) or any(
-        p.requires_grad for p in module.parameters())
+    if any(t.requires_grad for t in tensors if isinstance(t, torch.Tensor)):
+        return True
+    return module.training and any(p.requires_grad for p in module.parameters())
 
 
 class _netG(nn.Module):

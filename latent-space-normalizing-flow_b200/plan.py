@@ -92,6 +92,15 @@ class Plan:
     def _sig(tensors):
         return tuple((t.data_ptr(), t._version) for t in tensors)
 
+    def invalidate(self) -> None:
+        """Forget the packed parameters: the next call re-packs the generator and flow weights (and re-evaluates the
+        hoisted log|det W| / W^-1).  Packed copies are keyed on (data_ptr, Parameter._version); in-place edits through
+        ``.data`` (``p.data.copy_()``, EMA swaps, manual init -- the idiom the reference itself uses) do not bump the
+        version counter, so call this (or ``lsnf_b200.invalidate_plans()``) after such an edit."""
+        self._g_sig = None
+        self._f_sig = None
+        self._f_has_inv = False
+
     def ensure_generator(self, netG) -> None:
         convs = [m for m in netG.gen if isinstance(m, torch.nn.ConvTranspose2d)]
         ws = [m.weight for m in convs]
@@ -188,6 +197,17 @@ class Plan:
                                                    _stream(self.device)), "lsnf_flow_inverse")
         return z, negobj
 
+    def sample_prior(self, eps: torch.Tensor, to_unit_range: bool = True, want_z: bool = False):
+        """eps [B,nz] -> x = clamp((G(F^-1(eps)) + 1) / 2, 0, 1) in one C-ABI call (train.py:565-576)."""
+        _check_tensor(eps, "eps", self.device, (self.batch, self.nz))
+        x = torch.empty(self.batch, self.nc, self.img, self.img, dtype=torch.float32, device=self.device)
+        z = torch.empty_like(eps) if want_z else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.lsnf_sample_prior(self.handle, eps.data_ptr(), x.data_ptr(),
+                                                   z.data_ptr() if want_z else None, int(bool(to_unit_range)),
+                                                   _stream(self.device)), "lsnf_sample_prior")
+        return (x, z) if want_z else x
+
     def langevin_update(self, z, grad_g, grad_f, step_size, eps=None, with_noise=True, seed=0, sample_offset=0,
                         step=0, want_norms=True):
         for t, n in ((z, "z"), (grad_g, "grad_g"), (grad_f, "grad_f")):
@@ -226,15 +246,15 @@ _PLANS: Dict[Tuple, Plan] = {}
 def default_bwd_passes(noisy_chain: bool = False) -> int:
     """Tensor-core passes of the data-gradient stages (include/lsnf.h).
 
-    3 (hi/lo split) wherever the gradient itself is the result or the chain is noise-free and long (test mode:
-    a gradient error moves the fixed point).  1 (single fp16 pass, gradient to ~2e-4) for the short-run chains with
-    injected noise of training mode, where z_T stays within the 1e-4 parity budget (measured: 6e-5 at T=20, and the
-    gradient enters z scaled by s^2/2 = 0.005 next to noise of size s = 0.1).  LSNF_BWD_PASSES=1|3 overrides."""
+    Always 3 (bf16 hi|lo split, arithmetic not narrower than the reference's fp32 autograd) unless the caller opts
+    in to the single fp16 pass with ``bwd_passes=1`` / ``LSNF_BWD_PASSES=1``: that mode is ~1.4x faster end to end
+    but carries an 11-bit significand through the gradient (measured margins on z_T against the 1e-4 budget:
+    profiles/r2_parity_cifar10_b100_t40.json).  ``noisy_chain`` is kept for call compatibility and ignored."""
     import os
     env = os.environ.get("LSNF_BWD_PASSES")
     if env:
         return int(env)
-    return 1 if noisy_chain else 3
+    return 3
 
 
 def get_plan(*, arch, batch, nz, ngf, nc, f_depth, f_width, f_permutation, f_coupling, leak, device,
@@ -259,3 +279,9 @@ def get_plan(*, arch, batch, nz, ngf, nc, f_depth, f_width, f_permutation, f_cou
 
 def clear_plans():
     _PLANS.clear()
+
+
+def invalidate_plans():
+    """Re-pack the parameters of every cached plan at its next use (see ``Plan.invalidate``)."""
+    for p in _PLANS.values():
+        p.invalidate()

@@ -161,7 +161,8 @@ def flow_reverse(fp: Params, z: torch.Tensor, logdet: torch.Tensor, depth: int, 
 
 def log_prior(fp: Params, z: torch.Tensor, depth: int, coupling: int = 1, permutation: int = 2):
     """train.py:316-319: ll_b = sum_j(-0.5 z1^2) + log(2 pi) + logdet_b.  Returns (ll, z1, logdet)."""
-    z1, logdet = flow_forward(fp, z, torch.zeros(z.shape[0], dtype=z.dtype), depth, coupling, permutation)
+    z1, logdet = flow_forward(fp, z, torch.zeros(z.shape[0], dtype=z.dtype, device=z.device), depth, coupling,
+                              permutation)   # train.py:316: torch.zeros(B).to(device)
     ll = (-0.5 * z1 ** 2).flatten(1).sum(-1) + LOG_2PI + logdet
     return ll, z1, logdet
 

@@ -61,3 +61,48 @@ def assert_grad_close(got, want, tol=REL_TOL, what="gradient", kink_tol=3e-2):
     assert np.median(e) < tol, f"{what}: median per-sample rel-l2 {np.median(e):.3e} >= {tol}"
     assert e.max() < kink_tol, f"{what}: worst per-sample rel-l2 {e.max():.3e} >= {kink_tol}"
     return e
+
+
+def build_nets(c, device="cuda:0", impl=0, seed=1):
+    """(args, netG, netF) of the product modules with the deterministic synthetic parameters of ``synth`` loaded.
+    ``c``: dataset, nz, ngf[, f_width, coupling, permutation, sigma, T]."""
+    import lsnf_b200
+    from lsnf_b200 import synth
+    args = lsnf_b200.make_args(dataset=c["dataset"], nz=c["nz"], ngf=c["ngf"], f_width=c.get("f_width", 64),
+                               f_flow_coupling=c.get("coupling", 1), f_flow_permutation=c.get("permutation", 2),
+                               g_llhd_sigma=c.get("sigma", 0.3), g_l_steps=c.get("T", 20))
+    netG = lsnf_b200._netG(args).to(device).eval()
+    netF = lsnf_b200._netF(args, nz=c["nz"]).to(device).eval()
+    netG.load_state_dict(to_torch(synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=seed)))
+    netF.load_state_dict(to_torch(synth.flow_state(c["nz"], c.get("f_width", 64), 5, c.get("coupling", 1),
+                                                   c.get("permutation", 2), seed=seed)))
+    netG.gemm_impl = impl
+    return args, netG, netF
+
+
+def oracle_langevin(c, x_np, z0_np, eps_np, seed=1, steps=None, trace=None):
+    """The CPU oracle (oracle/refpath.py) on the same synthetic parameters and inputs; returns (z_T, |g|, |f|)."""
+    from lsnf_b200 import synth
+    from oracle import refpath
+    gp = to_torch(synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=seed))
+    fp = to_torch(synth.flow_state(c["nz"], c.get("f_width", 64), 5, c.get("coupling", 1), c.get("permutation", 2),
+                                   seed=seed))
+    layers = refpath.generator_layers(c["dataset"], c["nz"], c["ngf"])
+    eps = torch.from_numpy(eps_np) if eps_np is not None else None
+    return refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np), gp, fp, layers, depth=5,
+                            steps=c["T"] if steps is None else steps, step_size=0.1, sigma=c.get("sigma", 0.3),
+                            eps=eps, coupling=c.get("coupling", 1), permutation=c.get("permutation", 2), trace=trace)
+
+
+def record(name, obj):
+    """Drop a small JSON record under gpurun_out/ (merged back from the GPU box) so measured parity margins can be
+    committed under profiles/."""
+    import json
+    d = os.path.join(os.path.dirname(GOLDEN.rstrip("/")), "..", "gpurun_out")
+    d = os.path.normpath(d)
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name), "w") as f:
+            json.dump(obj, f, indent=1)
+    except OSError:
+        pass

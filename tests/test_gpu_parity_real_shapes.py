@@ -1,0 +1,149 @@
+"""Oracle parity at the REAL shapes of the BASELINE configurations, through the C ABI.
+
+The small fixtures of tests/golden never run more than one M tile; here the CUDA path is compared with the CPU oracle
+(oracle/refpath.py, pinned against the reference's own model.py by oracle/make_golden.py) at the widths and batch
+sizes the benchmark runs: multi-tile persistence, the 200/400-tile schedules, stream-K and the split-K first-layer
+gradient are all exercised.  Tolerance (north_star): z_T within 1e-4 relative (fp32) on identical inputs and injected
+noise; the shuffle permutation bit-exact.  Reference lines: train.py:307-335, model.py:214-225.
+"""
+import numpy as np
+import pytest
+import torch
+
+import lsnf_b200
+from lsnf_b200 import synth
+from oracle import philox
+from helpers import REL_TOL, build_nets, oracle_langevin, record, rel_err, rel_l2, to_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CIFAR = dict(dataset="cifar10", nz=128, ngf=128, f_width=64, sigma=0.3, T=40)
+
+
+def _gpu(a):
+    return torch.from_numpy(a).to(DEV)
+
+
+def test_cifar_headline_shape_multi_seed_against_oracle():
+    # (1a) B=100, T=40, injected noise, five seeds (parameters AND inputs reseeded), 3-pass and 1-pass data gradient.
+    # The fp32-equivalent 3-pass setting is the default and must hold 1e-4 on every seed; the single-pass fp16 data
+    # gradient is an explicit opt-in whose measured margin is recorded next to it.
+    table = []
+    for seed in (1, 2, 3, 4, 5):
+        c = dict(CIFAR, B=100)
+        x_np, z0_np, eps_np = synth.inputs(100, 128, 3, 32, 40, seed=100 + seed)
+        zr, gnr, fnr = oracle_langevin(c, x_np, z0_np, eps_np, seed=seed)
+        args, netG, netF = build_nets(c, DEV, seed=seed)
+        row = {"seed": seed}
+        for passes in (3, 1):
+            z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(_gpu(z0_np), _gpu(x_np), netG, netF, args,
+                                                                   eps=_gpu(eps_np), bwd_passes=passes)
+            row[f"z_T_rel_l2_bwd{passes}"] = rel_l2(z.cpu(), zr)
+            row[f"z_T_rel_max_bwd{passes}"] = rel_err(z.cpu(), zr)
+            row[f"gnorm_g_rel_bwd{passes}"] = abs(gn.item() - gnr.item()) / gnr.item()
+        table.append(row)
+        print(row)
+    record("parity_cifar10_b100_t40.json", {"config": CIFAR, "batch": 100, "rows": table, "tolerance": REL_TOL})
+    assert max(r["z_T_rel_l2_bwd3"] for r in table) < REL_TOL
+    assert max(r["z_T_rel_l2_bwd1"] for r in table) < 2 * REL_TOL   # opt-in reduced-precision mode: recorded, looser
+
+
+@pytest.mark.parametrize("name,c,B,T", [
+    ("svhn", dict(dataset="svhn", nz=100, ngf=64, f_width=64, sigma=0.3), 100, 20),
+    ("celeba_crop", dict(dataset="celeba_crop", nz=100, ngf=128, f_width=64, sigma=0.3), 100, 2),
+    ("celeba_hq256", dict(dataset="celeba_hq256", nz=100, ngf=128, f_width=128, sigma=1.0), 8, 1),
+])
+def test_baseline_configs_at_true_widths_against_oracle(name, c, B, T):
+    # (1b) configs 1, 3, 5 at the channel widths / batch sizes BASELINE.json names (different ngf means different N
+    # tiles, ring geometries and pair / 1-CTA kernel choices than the small fixtures)
+    c = dict(c, T=T)
+    img = synth.image_size(c["dataset"])
+    x_np, z0_np, eps_np = synth.inputs(B, c["nz"], 3, img, T, seed=17)
+    zr, gnr, fnr = oracle_langevin(c, x_np, z0_np, eps_np, seed=3)
+    args, netG, netF = build_nets(c, DEV, seed=3)
+    z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(_gpu(z0_np), _gpu(x_np), netG, netF, args, eps=_gpu(eps_np))
+    e = rel_l2(z.cpu(), zr)
+    print(f"{name}: B={B} T={T} z_T rel-l2 {e:.2e}, |grad_g| {gn.item():.4f} (oracle {gnr.item():.4f}), "
+          f"|grad_f| {fn.item():.4f} (oracle {fnr.item():.4f})")
+    record(f"parity_{name}_true_width.json", {"config": c, "batch": B, "steps": T, "z_T_rel_l2": e})
+    assert e < REL_TOL
+    assert abs(gn.item() - gnr.item()) < 2e-3 * gnr.item() and abs(fn.item() - fnr.item()) < 1e-3 * fnr.item()
+    # noise-free (test-mode) variant at the same shape
+    zr0, _, _ = oracle_langevin(c, x_np, z0_np, None, seed=3)
+    z0_, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(_gpu(z0_np), _gpu(x_np), netG, netF, args, with_noise=False)
+    assert rel_l2(z0_.cpu(), zr0) < REL_TOL
+
+
+@pytest.mark.parametrize("c,B,T", [
+    (dict(dataset="svhn", nz=100, ngf=64, f_width=64, sigma=0.3), 100, 20),
+    (dict(CIFAR), 100, 10),
+])
+def test_product_configuration_philox_graph_replay_against_oracle(c, B, T):
+    # (1c) what a user runs: no injected noise, in-kernel Philox keyed by (seed, global sample, step), and from the
+    # second call of a plan the CUDA-graph replay.  The oracle is fed the same noise from oracle/philox.py.
+    c = dict(c, T=T)
+    img = synth.image_size(c["dataset"])
+    x_np, z0_np, _ = synth.inputs(B, c["nz"], 3, img, 1, seed=23)
+    seed, offset = 0x5EED00000000 + 77, 4000
+    eps_np = np.stack([philox.langevin_noise(seed, offset, B, c["nz"], t) for t in range(T)]).reshape(T, B, c["nz"], 1, 1)
+    zr, gnr, fnr = oracle_langevin(c, x_np, z0_np, eps_np.astype(np.float32), seed=2)
+    args, netG, netF = build_nets(c, DEV, seed=2)
+    outs = []
+    for call in range(3):   # call 0 runs eagerly, calls 1-2 replay the captured graph
+        z, gn, fn = lsnf_b200.sample_langevin_post_z_with_flow(_gpu(z0_np), _gpu(x_np), netG, netF, args, seed=seed,
+                                                               sample_offset=offset)
+        outs.append(z.cpu())
+        e = rel_l2(z.cpu(), zr)
+        print(f"{c['dataset']} philox call {call}: z_T rel-l2 vs oracle {e:.2e}")
+        assert e < REL_TOL
+        assert abs(gn.item() - gnr.item()) < 2e-3 * gnr.item()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])   # eager == graph replay, bit for bit
+
+
+def test_shuffle_permutation_gather_is_bit_exact_forward_and_inverse():
+    # (1d) A7: with actnorm b = logs = 0, additive coupling and an all-zero fc_zeros the flow is nothing but the
+    # fixed channel permutations: (x + 0) * exp(0) and z2 + 0 are exact, so the CUDA output must EQUAL the
+    # index_select chain bit for bit -- forward and inverse (model.py:214-225, intended semantics).
+    nz, B = 100, 133
+    args = lsnf_b200.make_args(nz=nz, f_flow_permutation=1, f_flow_coupling=0)
+    sd = synth.flow_state(nz, 64, 5, 0, 1, seed=5)
+    for k in list(sd):
+        if k.endswith("actnorm.b") or k.endswith("actnorm.bias") or k.endswith("actnorm.logs"):
+            if ".f.fc_" not in k:
+                sd[k] = np.zeros_like(sd[k])
+        if "fc_zeros" in k:
+            sd[k] = np.zeros_like(sd[k])
+    netF = lsnf_b200._netF(args, nz=nz).to(DEV).eval()
+    netF.load_state_dict(to_torch(sd))
+    z = torch.randn(B, nz, device=DEV, generator=torch.Generator(DEV).manual_seed(9))
+    z1, logdet, logp, _ = netF.log_prior(z)
+    want = z.cpu()
+    for i in range(5):
+        want = want.index_select(1, torch.from_numpy(sd[f"revnet2d_s.0.revnet2d_step_s.{i}.shuffle_features.indices"]).long())
+    assert torch.equal(z1.cpu(), want), "forward shuffle must be pure data movement"
+    assert torch.equal(logdet.cpu(), torch.zeros(B))
+    back, negobj = netF.inverse(z1)
+    assert torch.equal(back.cpu(), z.cpu()), "inverse shuffle must restore the input bit for bit"
+    inv = want
+    for i in reversed(range(5)):
+        inv = inv.index_select(1, torch.from_numpy(sd[f"revnet2d_s.0.revnet2d_step_s.{i}.shuffle_features.indices_inverse"]).long())
+    assert torch.equal(inv, z.cpu())
+    # reference module signature (model.py:473-498)
+    with torch.no_grad():
+        zo, obj, _ = netF(z, objective=torch.zeros(B, device=DEV))
+    assert torch.equal(zo.cpu(), want)
+
+
+def test_small_sigma_does_not_overflow_the_gradient_tensors():
+    # the loss-gradient seed carries 1/sigma^2; with --g_llhd_sigma 0.01 that is 1e4 and must neither
+    # overflow a 16-bit gradient tensor nor lose parity (default 3-pass bf16 hi|lo gradient has fp32 range)
+    c = dict(dataset="svhn", nz=100, ngf=64, f_width=64, sigma=0.01, T=1)
+    x_np, z0_np, eps_np = synth.inputs(16, 100, 3, 32, 1, seed=31)
+    zr, gnr, _ = oracle_langevin(c, x_np, z0_np, eps_np, seed=1)
+    args, netG, netF = build_nets(c, DEV, seed=1)
+    for passes in (3, 1):
+        z, gn, _ = lsnf_b200.sample_langevin_post_z_with_flow(_gpu(z0_np), _gpu(x_np), netG, netF, args,
+                                                              eps=_gpu(eps_np), bwd_passes=passes)
+        assert torch.isfinite(z).all()
+        assert rel_l2(z.cpu(), zr) < (REL_TOL if passes == 3 else 1e-3), passes

@@ -173,7 +173,10 @@ def test_compute_entry_points_fail_loudly_without_binding():
     assert lib.lsnf_generator_forward(h, None, None, None) == -3          # LSNF_ERR_STATE: not bound
     assert b"bind" in lib.lsnf_last_error()
     assert lib.lsnf_workspace_bytes(h) > 0
-    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 3)
+    # split_z + per iteration (4 forward + fused last-layer kernel + 4 data-gradient + flow + update) + one
+    # set-dyn kernel per replayed graph chunk of 40 iterations
+    assert lib.lsnf_langevin_launch_count(h, 20) == 1 + 20 * (2 * 4 + 3) + 1
+    assert lib.lsnf_langevin_launch_count(h, 8000) == 1 + 8000 * (2 * 4 + 3) + 200
     lib.lsnf_plan_destroy(h)
 
 
