@@ -12,6 +12,8 @@
  *   lsnf_langevin_update     <- z update + noise + diagnostics            train.py:324-329
  *   lsnf_langevin_run        <- sample_langevin_post_z_with_flow          train.py:307-335, :602-634
  *   lsnf_sample_prior        <- sample_x(): eps -> F^-1 -> G -> [0,1]     train.py:565-576, :433-437, :472-478
+ *   lsnf_flow_param_grads    <- loss_f = -ll.mean(); loss_f.backward()    train.py:403-411, model.py:182
+ *   lsnf_adam_step           <- optG.step() / optF.step() (torch.optim.Adam) train.py:294-295, :398, :415
  *   lsnf_pack_*              <- parameters of _netG / _netF               model.py:48-157, :460-498
  *
  * Conventions: every function returns 0 on success and a negative lsnf_status otherwise;
@@ -149,6 +151,29 @@ int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t 
  * x = clamp((G(z) + 1) / 2, 0, 1).  z (nullable) receives the latents [B,nz].  eps is not modified.  Needs flow
  * weights packed with w_inverse. */
 int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int32_t to_unit_range, lsnf_stream stream);
+/* ---- parameter updates (training mode) ---------------------------------------------------------------- */
+/* Flow parameter gradients of loss_f = -(1 / global_batch) * sum_b ll_b(z_b) over this plan's batch z [B,nz]
+ * (train.py:403-411; ll_b = log p(z_b) of lsnf_flow_forward).  grads: device buffer of lsnf_flow_grad_floats()
+ * floats, ZERO-INITIALISED by the caller once (alignment padding is never written); tensor (step, i) -- i in the order
+ * of LSNF_FLOW_PTRS_PER_STEP -- occupies [offsets[step*12+i], +sizes[step*12+i]) in its natural row-major shape
+ * (lsnf_flow_grad_layout).  With several ranks each passes its shard and the GLOBAL batch size; the buffers are then
+ * summed (one all-reduce).  d log|det W| / dW = W^-T (model.py:182) uses the W^-1 given to lsnf_pack_flow_weights.
+ * loss (nullable, device float): this rank's share of loss_f.  Deterministic (fixed summation order). */
+size_t lsnf_flow_grad_floats(const lsnf_plan* plan);
+int lsnf_flow_grad_layout(const lsnf_plan* plan, int64_t* offsets, int64_t* sizes);
+int lsnf_flow_param_grads(lsnf_plan* plan, const float* z, int32_t global_batch, float* grads, float* loss,
+                          lsnf_stream stream);
+/* Fused multi-tensor Adam, semantics of torch.optim.Adam (no amsgrad; weight_decay is added to the gradient):
+ * for each of n_tensors fp32 device tensors  g' = g * (*grad_scale) + weight_decay * p;  m = lerp(m, g', 1-beta1);
+ * v = beta2 v + (1-beta2) g'^2;  p -= lr / (1-beta1^step) * m / (sqrt(v) / sqrt(1-beta2^step) + eps).
+ * `step` is the 1-based count AFTER this update.  grad_scale: nullable device scalar (gradient-norm clipping).
+ * grad_kk / grad_inner (nullable): gradient i is stored tap-major [kk][outer][inner] for a parameter laid out
+ * [outer][inner][kk] (ConvTranspose2d weights); kk <= 1 means same layout as the parameter.  No plan needed. */
+int lsnf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* sizes, const int32_t* grad_kk, const int32_t* grad_inner,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                   const float* grad_scale, lsnf_stream stream);
+
 /* Launches generator stage `index` alone (0..L-1 forward, L..2L-1 data gradient) on the buffers currently in the
  * workspace.  Profiling / test hook: bench.py times the dominant tap-GEMM with CUDA events through it. */
 int lsnf_plan_run_stage(lsnf_plan* plan, int32_t index, lsnf_stream stream);

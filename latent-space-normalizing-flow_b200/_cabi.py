@@ -73,6 +73,13 @@ EXPORTS = {
     "lsnf_langevin_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsnf_sample_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "lsnf_flow_grad_floats": (C.c_size_t, [C.c_void_p]),
+    "lsnf_flow_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lsnf_flow_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsnf_adam_step": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int64, C.c_void_p, C.c_void_p]),
     "lsnf_plan_run_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "lsnf_langevin_launch_count": (C.c_int, [C.c_void_p, C.c_int32]),
     "lsnf_plan_num_stages": (C.c_int, [C.c_void_p]),

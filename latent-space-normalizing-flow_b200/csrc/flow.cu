@@ -20,6 +20,8 @@ struct FlowArgs {
   float* logp;
   float* grad;
   uint32_t ring_floats;  // shared-memory ring that streams the matrices
+  float* stash;          // TRAIN instantiation: per-layer, per-sample vectors the parameter gradients are built from
+  FlowStash sl;
 };
 
 constexpr int FLOW_THREADS = 256;
@@ -257,7 +259,16 @@ __device__ __forceinline__ void block_sum(float (&v)[S], float* red) {
 
 #define AT(buf, s, j) (buf)[(j) * S + (s)]
 
-template <int S>
+// element (layer L, slot offset `slot`, sample b, feature j) of the training stash
+__device__ __forceinline__ float* stash_at(const FlowArgs& a, int L, size_t slot, int dim, int b, int j) {
+  return a.stash + (size_t)L * a.sl.layer_floats * a.B + slot * a.B + (size_t)b * dim + j;
+}
+
+// TRAIN = true (flow parameter update, train.py:403-415): the same forward + analytic backward, additionally
+// writing for every step and sample the vectors whose batch outer products are the parameter gradients
+// (flow_param_grad_kernel): layer inputs y, u1, a1, a2, the MLP output h, the gradients w.r.t. the four matmul
+// outputs g_u, g_p1, g_p2, g_p3, w.r.t. the step input g_x, and the per-element log-scale terms gl0..gl3.
+template <int S, bool TRAIN>
 __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) {
   extern __shared__ __align__(16) float sm[];
   const FlowLayout& f = a.fl;
@@ -295,6 +306,12 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
       ta[i] = (cur[i] + P[f.an_b + j]) * P[f.an_e + j];
     }
     __syncthreads();
+    if constexpr (TRAIN) {
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+        const int s = i / nz, j = i % nz;
+        if (s < ns) *stash_at(a, L, a.sl.y, nz, b0 + s, j) = AT(ta, s, j);
+      }
+    }
     if (a.permutation == 2) {   // model.py:187: z @ W
       matvec<S>(fd.next_mat(), nz, nz, ta, scratch, [&](int s, int j, float v) { AT(cur, s, j) = v; });
     } else {                    // intended shuffle_features: h[:, idx]
@@ -305,6 +322,12 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < S; ++s) ld[s] += P[f.ld_const] , ld[s] += P[f.ld_const + 1];
+    }
+    if constexpr (TRAIN) {
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i / half, j = i % half;
+        if (s < ns) *stash_at(a, L, a.sl.u1, half, b0 + s, j) = AT(cur, s, j);
+      }
     }
     // coupling MLP on x1 = cur[:half] (model.py:306-310)
     float* a1 = st;             // [w][S]
@@ -317,6 +340,19 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
               [&](int s, int j, float v) { AT(a2, s, j) = fmaxf((v + P[f.b2 + j]) * P[f.e2 + j], 0.f); });
     matvec<S>(fd.next_mat(), w, n_out, a2, scratch,
               [&](int s, int j, float v) { AT(ta, s, j) = (v + P[f.b3 + j]) * P[f.e3 + j]; });
+    if constexpr (TRAIN) {
+      for (int i = tid; i < S * w; i += FLOW_THREADS) {
+        const int s = i / w, j = i % w;
+        if (s < ns) {
+          *stash_at(a, L, a.sl.a1, w, b0 + s, j) = AT(a1, s, j);
+          *stash_at(a, L, a.sl.a2, w, b0 + s, j) = AT(a2, s, j);
+        }
+      }
+      for (int i = tid; i < S * n_out; i += FLOW_THREADS) {
+        const int s = i / n_out, j = i % n_out;
+        if (s < ns) *stash_at(a, L, a.sl.h, n_out, b0 + s, j) = AT(ta, s, j);
+      }
+    }
     float* x2 = cur + S * half;   // [half][S]
     if (a.coupling == 1) {      // model.py:410-418
       for (int i = tid; i < S * half; i += FLOW_THREADS) {
@@ -380,28 +416,85 @@ __global__ void __launch_bounds__(FLOW_THREADS) flow_forward_kernel(FlowArgs a) 
         const float g2 = g2p[i], scale = sc[i];
         const float g_shift = g2 * scale;
         const float g_scale = g2 * xs[i] - 1.f / scale;
-        AT(ta, s, 2 * j) = g_shift * P[f.e3 + 2 * j];
-        AT(ta, s, 2 * j + 1) = g_scale * scale * (1.f - scale) * P[f.e3 + 2 * j + 1];
+        const float gh0 = g_shift, gh1 = g_scale * scale * (1.f - scale);
+        AT(ta, s, 2 * j) = gh0 * P[f.e3 + 2 * j];
+        AT(ta, s, 2 * j + 1) = gh1 * P[f.e3 + 2 * j + 1];
         g2p[i] = g_shift;  // = g_x2
+        if constexpr (TRAIN) {
+          if (s < ns) {   // d/dlogs of h = (p + b) * exp(3 logs) is 3 h (model.py:348)
+            const float* hrow = stash_at(a, L, a.sl.h, n_out, b0 + s, 2 * j);
+            float* gl = stash_at(a, L, a.sl.gl3, n_out, b0 + s, 2 * j);
+            gl[0] = 3.f * gh0 * hrow[0];
+            gl[1] = 3.f * gh1 * hrow[1];
+          }
+        }
       }
     } else {
-      for (int i = tid; i < S * half; i += FLOW_THREADS) ta[i] = g2p[i] * P[f.e3 + i / S];
+      for (int i = tid; i < S * half; i += FLOW_THREADS) {
+        const int s = i % S, j = i / S;
+        const float gh = g2p[i];
+        ta[i] = gh * P[f.e3 + j];
+        if constexpr (TRAIN) {
+          if (s < ns) *stash_at(a, L, a.sl.gl3, n_out, b0 + s, j) = 3.f * gh * *stash_at(a, L, a.sl.h, n_out, b0 + s, j);
+        }
+      }
     }
     __syncthreads();
-    matvec<S>(fd.next_mat(), n_out, w, ta, scratch,
-              [&](int s, int j, float v) { AT(tb, s, j) = AT(a2, s, j) > 0.f ? v * P[f.e2 + j] : 0.f; });
-    matvec<S>(fd.next_mat(), w, w, tb, scratch,
-              [&](int s, int j, float v) { AT(ta, s, j) = AT(a1, s, j) > 0.f ? v * P[f.e1 + j] : 0.f; });
+    if constexpr (TRAIN) {
+      for (int i = tid; i < S * n_out; i += FLOW_THREADS) {
+        const int s = i / n_out, j = i % n_out;
+        if (s < ns) *stash_at(a, L, a.sl.gp3, n_out, b0 + s, j) = AT(ta, s, j);
+      }
+    }
+    matvec<S>(fd.next_mat(), n_out, w, ta, scratch, [&](int s, int j, float v) {
+      const float act = AT(a2, s, j);
+      const float gq = act > 0.f ? v : 0.f;   // gradient w.r.t. the actnorm output of fc_2 (ReLU mask applied)
+      AT(tb, s, j) = gq * P[f.e2 + j];
+      if constexpr (TRAIN) {
+        if (s < ns) {
+          *stash_at(a, L, a.sl.gp2, w, b0 + s, j) = gq * P[f.e2 + j];
+          *stash_at(a, L, a.sl.gl2, w, b0 + s, j) = 3.f * gq * act;
+        }
+      }
+    });
+    matvec<S>(fd.next_mat(), w, w, tb, scratch, [&](int s, int j, float v) {
+      const float act = AT(a1, s, j);
+      const float gq = act > 0.f ? v : 0.f;
+      AT(ta, s, j) = gq * P[f.e1 + j];
+      if constexpr (TRAIN) {
+        if (s < ns) {
+          *stash_at(a, L, a.sl.gp1, w, b0 + s, j) = gq * P[f.e1 + j];
+          *stash_at(a, L, a.sl.gl1, w, b0 + s, j) = 3.f * gq * act;
+        }
+      }
+    });
     matvec<S>(fd.next_mat(), w, half, ta, scratch, [&](int s, int j, float v) { AT(g, s, j) += v; });
     for (int i = tid; i < S * nz; i += FLOW_THREADS) ta[i] = g[i];
     __syncthreads();
+    if constexpr (TRAIN) {
+      for (int i = tid; i < S * nz; i += FLOW_THREADS) {
+        const int s = i / nz, j = i % nz;
+        if (s < ns) *stash_at(a, L, a.sl.gu, nz, b0 + s, j) = AT(ta, s, j);
+      }
+    }
+    // g_y = g_u @ W^T (or the inverse shuffle), g_x = g_y * exp(3 logs); d/dlogs of y = (x + b) exp(3 logs) is 3 y
+    auto actnorm_bwd = [&](int s, int j, float gy) {
+      const float gx = gy * P[f.an_e + j];
+      AT(g, s, j) = gx;
+      if constexpr (TRAIN) {
+        if (s < ns) {
+          *stash_at(a, L, a.sl.gx, nz, b0 + s, j) = gx;
+          *stash_at(a, L, a.sl.gl0, nz, b0 + s, j) = 3.f * gy * *stash_at(a, L, a.sl.y, nz, b0 + s, j);
+        }
+      }
+    };
     if (a.permutation == 2) {   // g @ W^T, then the actnorm scale
-      matvec<S>(fd.next_mat(), nz, nz, ta, scratch, [&](int s, int j, float v) { AT(g, s, j) = v * P[f.an_e + j]; });
+      matvec<S>(fd.next_mat(), nz, nz, ta, scratch, actnorm_bwd);
     } else {
       const int* inv = reinterpret_cast<const int*>(P + f.perm_inv);
       for (int i = tid; i < S * nz; i += FLOW_THREADS) {
         const int s = i % S, j = i / S;
-        g[i] = AT(ta, s, inv[j]) * P[f.an_e + j];
+        actnorm_bwd(s, j, AT(ta, s, inv[j]));
       }
       __syncthreads();
     }
@@ -603,7 +696,10 @@ static int flow_ring_floats(const FlowLayout& f, size_t fixed, int depth, bool b
 
 template <int S>
 static int launch_fwd_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
-  flow_forward_kernel<S><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
+  if (a.stash)
+    flow_forward_kernel<S, true><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
+  else
+    flow_forward_kernel<S, false><<<(a.B + S - 1) / S, FLOW_THREADS, smem, s>>>(a);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }
@@ -614,6 +710,22 @@ static int launch_inv_t(const FlowArgs& a, size_t smem, cudaStream_t s) {
   return LSNF_OK;
 }
 
+static int launch_flow_fwd_args(FlowArgs& a, cudaStream_t s) {
+  const int S = pick_s(a.B);
+  const size_t fixed = flow_fixed_floats(a.fl, S, a.depth, true);
+  if (flow_ring_floats(a.fl, fixed, a.depth, a.grad != nullptr, &a.ring_floats)) {
+    set_error("flow kernel shared memory budget exceeded");
+    return LSNF_ERR_INVALID;
+  }
+  const size_t smem = (fixed + a.ring_floats) * 4;
+  switch (S) {
+    case 1: return launch_fwd_t<1>(a, smem, s);
+    case 2: return launch_fwd_t<2>(a, smem, s);
+    case 4: return launch_fwd_t<4>(a, smem, s);
+    default: return launch_fwd_t<8>(a, smem, s);
+  }
+}
+
 // opt-in shared-memory limit of every instantiation, once per device (lsnf_plan_bind)
 int flow_prepare_device(int device) {
   static std::mutex mu;
@@ -622,10 +734,14 @@ int flow_prepare_device(int device) {
   if (device < 0 || device >= 64) { set_error("device index out of range"); return LSNF_ERR_INVALID; }
   if (done[device]) return LSNF_OK;
   const int lim = 227 * 1024;
-  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_forward_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -641,19 +757,140 @@ int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, flo
   a.fl = plan->fl; a.depth = plan->cfg.f_depth; a.B = plan->cfg.batch;
   a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
   a.in = z; a.z_out = z_out; a.logdet = logdet; a.logp = logp; a.grad = grad_z;
-  const int S = pick_s(a.B);
-  const size_t fixed = flow_fixed_floats(a.fl, S, a.depth, true);
-  if (flow_ring_floats(a.fl, fixed, a.depth, grad_z != nullptr, &a.ring_floats)) {
-    set_error("flow kernel shared memory budget exceeded");
-    return LSNF_ERR_INVALID;
+  a.stash = nullptr;
+  return launch_flow_fwd_args(a, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// flow parameter gradients (train.py:403-411): loss_f = -(1 / B_global) sum_b ll_b.  After the TRAIN instantiation
+// of the fused kernel has left the per-sample vectors in the stash, every parameter gradient is a reduction over
+// the batch: matrices dM[k][n] = sum_b X[b][k] G[b][n], vectors = column sums.
+//   d invertible_1x1_conv.w = y^T g_u - B_local * W^-T     (d log|det W| / dW = W^-T, model.py:182)
+//   d actnorm.b = colsum(g_x),  d actnorm.logs = colsum(gl0) - 3 B_local   (logdet += sum 3 logs, model.py:273-276)
+//   d fc_k.w = in_k^T g_pk,  d fc_k.actnorm.b = colsum(g_pk),  d fc_k.actnorm.logs = colsum(gl_k)   (k = 1, 2)
+//   d fc_zeros.w = a2^T g_p3,  d fc_zeros.b = colsum(g_p3),  d fc_zeros.logs = colsum(gl3)
+// all multiplied by 1 / B_global.  Summation over the batch is in a fixed order: deterministic.
+// Grid: (row blocks of the four matrices + 4 vector CTAs + 1 loss CTA, f_depth).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PG_ROWS = 8;   // matrix rows per CTA
+
+struct ParamGradArgs {
+  const float* stash;
+  const float* params;   // packed flow parameters (W^-1 of every step)
+  const float* logp;     // [B]
+  float* grads;          // flat, FlowGradLayout per step
+  float* loss;           // -(1 / B_global) sum_b logp_b
+  FlowLayout fl;
+  FlowStash sl;
+  FlowGradLayout gl;
+  int B, permutation, blocks_w, blocks_w1, blocks_w2, blocks_w3;
+  float inv_bg;
+};
+
+__device__ __forceinline__ void pg_matrix(const float* X, int K, const float* G, int N, int B, int k0, float scale,
+                                          float* out, const float* winv, int nz, float winv_coef) {
+  // rows [k0, k0 + PG_ROWS) of out[K][N] = scale * (sum_b X[b][k] G[b][n] + winv_coef * Winv[n][k])
+  const int rows = min(PG_ROWS, K - k0);
+  for (int o = threadIdx.x; o < rows * N; o += blockDim.x) {
+    const int k = k0 + o / N, n = o % N;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) acc = fmaf(__ldg(X + (size_t)b * K + k), __ldg(G + (size_t)b * N + n), acc);
+    if (winv) acc += winv_coef * winv[(size_t)n * nz + k];
+    out[(size_t)k * N + n] = acc * scale;
   }
-  const size_t smem = (fixed + a.ring_floats) * 4;
-  switch (S) {
-    case 1: return launch_fwd_t<1>(a, smem, s);
-    case 2: return launch_fwd_t<2>(a, smem, s);
-    case 4: return launch_fwd_t<4>(a, smem, s);
-    default: return launch_fwd_t<8>(a, smem, s);
+}
+
+__device__ __forceinline__ void pg_colsum(const float* V, int N, int B, float scale, float add, float* out) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += __ldg(V + (size_t)b * N + n);
+    out[n] = (acc + add) * scale;
   }
+}
+
+__global__ void __launch_bounds__(256) flow_param_grad_kernel(ParamGradArgs a) {
+  const int L = blockIdx.y;
+  const FlowLayout& f = a.fl;
+  const int nz = f.nz, w = f.w, half = f.half, n_out = f.n_out, B = a.B;
+  const float* st = a.stash + (size_t)L * a.sl.layer_floats * B;
+  auto slot = [&](size_t off) { return st + off * B; };
+  float* g = a.grads + (size_t)L * a.gl.step_floats;
+  int blk = blockIdx.x;
+  if (blk < a.blocks_w) {
+    if (a.permutation == 2)
+      pg_matrix(slot(a.sl.y), nz, slot(a.sl.gu), nz, B, blk * PG_ROWS, a.inv_bg, g + a.gl.off[2],
+                a.params + (size_t)L * f.step_floats + f.Winv, nz, -(float)B);
+    return;
+  }
+  blk -= a.blocks_w;
+  if (blk < a.blocks_w1) {
+    pg_matrix(slot(a.sl.u1), half, slot(a.sl.gp1), w, B, blk * PG_ROWS, a.inv_bg, g + a.gl.off[3], nullptr, 0, 0.f);
+    return;
+  }
+  blk -= a.blocks_w1;
+  if (blk < a.blocks_w2) {
+    pg_matrix(slot(a.sl.a1), w, slot(a.sl.gp2), w, B, blk * PG_ROWS, a.inv_bg, g + a.gl.off[6], nullptr, 0, 0.f);
+    return;
+  }
+  blk -= a.blocks_w2;
+  if (blk < a.blocks_w3) {
+    pg_matrix(slot(a.sl.a2), w, slot(a.sl.gp3), n_out, B, blk * PG_ROWS, a.inv_bg, g + a.gl.off[9], nullptr, 0, 0.f);
+    return;
+  }
+  blk -= a.blocks_w3;
+  if (blk == 0) {
+    pg_colsum(slot(a.sl.gx), nz, B, a.inv_bg, 0.f, g + a.gl.off[0]);
+    pg_colsum(slot(a.sl.gl0), nz, B, a.inv_bg, -3.f * (float)B, g + a.gl.off[1]);
+  } else if (blk == 1) {
+    pg_colsum(slot(a.sl.gp1), w, B, a.inv_bg, 0.f, g + a.gl.off[4]);
+    pg_colsum(slot(a.sl.gl1), w, B, a.inv_bg, 0.f, g + a.gl.off[5]);
+  } else if (blk == 2) {
+    pg_colsum(slot(a.sl.gp2), w, B, a.inv_bg, 0.f, g + a.gl.off[7]);
+    pg_colsum(slot(a.sl.gl2), w, B, a.inv_bg, 0.f, g + a.gl.off[8]);
+  } else if (blk == 3) {
+    pg_colsum(slot(a.sl.gp3), n_out, B, a.inv_bg, 0.f, g + a.gl.off[10]);
+    pg_colsum(slot(a.sl.gl3), n_out, B, a.inv_bg, 0.f, g + a.gl.off[11]);
+  } else if (L == 0 && a.loss) {
+    // loss_f = -mean_b ll_b over the global batch (this rank's partial sum), fixed-order tree
+    __shared__ float red[256];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) acc += a.logp[b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) *a.loss = -red[0] * a.inv_bg;
+  }
+}
+
+int launch_flow_param_grads(const lsnf_plan* plan, const float* z, float inv_global_batch, float* grads, float* loss,
+                            cudaStream_t s) {
+  FlowArgs a;
+  a.params = (const float*)(plan->ws + plan->off_flow);
+  a.fl = plan->fl; a.depth = plan->cfg.f_depth; a.B = plan->cfg.batch;
+  a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
+  float* fo = (float*)(plan->ws + plan->off_flow_out);   // z_out [B][nz], logdet [B], logp [B]
+  a.in = z; a.z_out = nullptr; a.logdet = nullptr; a.logp = fo + (size_t)a.B * a.fl.nz + a.B;
+  a.grad = (float*)(plan->ws + plan->off_gradf);         // the kernel's backward needs a destination; unused here
+  a.stash = (float*)(plan->ws + plan->off_fstash);
+  a.sl = plan->fstash;
+  int rc = launch_flow_fwd_args(a, s);
+  if (rc) return rc;
+  ParamGradArgs p;
+  p.stash = a.stash; p.params = a.params; p.logp = a.logp; p.grads = grads; p.loss = loss;
+  p.fl = plan->fl; p.sl = plan->fstash; p.gl = plan->fgrad;
+  p.B = a.B; p.permutation = a.permutation; p.inv_bg = inv_global_batch;
+  p.blocks_w = (a.fl.nz + PG_ROWS - 1) / PG_ROWS;
+  p.blocks_w1 = (a.fl.half + PG_ROWS - 1) / PG_ROWS;
+  p.blocks_w2 = (a.fl.w + PG_ROWS - 1) / PG_ROWS;
+  p.blocks_w3 = (a.fl.w + PG_ROWS - 1) / PG_ROWS;
+  dim3 grid(p.blocks_w + p.blocks_w1 + p.blocks_w2 + p.blocks_w3 + 5, a.depth);
+  flow_param_grad_kernel<<<grid, 256, 0, s>>>(p);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
 }
 
 int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s) {
@@ -661,7 +898,7 @@ int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float
   a.params = (const float*)(plan->ws + plan->off_flow);
   a.fl = plan->fl; a.depth = plan->cfg.f_depth; a.B = plan->cfg.batch;
   a.coupling = plan->cfg.f_coupling; a.permutation = plan->cfg.f_permutation;
-  a.in = eps; a.z_out = z; a.logdet = negobj; a.logp = nullptr; a.grad = nullptr;
+  a.in = eps; a.z_out = z; a.logdet = negobj; a.logp = nullptr; a.grad = nullptr; a.stash = nullptr;
   const int S = pick_s(a.B);
   const size_t fixed = flow_fixed_floats(a.fl, S, a.depth, false);
   if (flow_ring_floats(a.fl, fixed, a.depth, false, &a.ring_floats)) {

@@ -92,6 +92,22 @@ struct FlowLayout {
   size_t max_mat;     // floats of the largest matrix
 };
 
+// Training stash of the flow prior (flow parameter update, train.py:403-415): per step, per slot a [B][dim] block.
+// Offsets are cumulative dims ("floats per sample before this slot"); element (L, slot, b, j) sits at
+// L * layer_floats * B + slot * B + b * dim + j.
+struct FlowStash {
+  size_t y, u1, a1, a2, h, gu, gp1, gp2, gp3, gx, gl0, gl1, gl2, gl3;
+  size_t layer_floats;
+};
+
+// Flat parameter-gradient layout of one flow step (floats), in the order of LSNF_FLOW_PTRS_PER_STEP:
+// actnorm.b, actnorm.logs, W, fc_1.w, fc_1.actnorm.b, fc_1.actnorm.logs, fc_2.w, ..., fc_zeros.w, .b, .logs
+struct FlowGradLayout {
+  size_t off[LSNF_FLOW_PTRS_PER_STEP];
+  size_t size[LSNF_FLOW_PTRS_PER_STEP];
+  size_t step_floats;
+};
+
 }  // namespace lsnf
 
 struct lsnf_plan {
@@ -103,6 +119,9 @@ struct lsnf_plan {
   struct Layer { int ci, co, k, s, p, hin, hout; } layers[8];
   std::vector<lsnf::StageHost> stages;  // forward stages 0..L-1, then data-gradient stages L-1..0
   lsnf::FlowLayout fl;
+  lsnf::FlowStash fstash;
+  lsnf::FlowGradLayout fgrad;
+  size_t off_fstash = 0, off_fgrad = 0, off_floss = 0;
   // workspace layout (byte offsets)
   size_t ws_bytes = 0;
   size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_mbits[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
@@ -180,6 +199,11 @@ int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t*
 int launch_flow_forward(const lsnf_plan* plan, const float* z, float* z_out, float* logdet, float* logp,
                         float* grad_z, cudaStream_t s);
 int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float* negobj, cudaStream_t s);
+int launch_adam(int n, float* const* params, const float* const* grads, float* const* m, float* const* v,
+                const int64_t* sizes, const int32_t* grad_kk, const int32_t* grad_inner, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int64_t step, const float* grad_scale, cudaStream_t s);
+int launch_flow_param_grads(const lsnf_plan* plan, const float* z, float inv_global_batch, float* grads, float* loss,
+                            cudaStream_t s);
 int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit, float gscale,
                   const float* gf, float step, const float* eps, int with_noise, uint64_t seed,
                   uint64_t sample_offset, uint32_t step_idx, const uint64_t* dyn, float* gnorms,

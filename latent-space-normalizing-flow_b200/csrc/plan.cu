@@ -204,6 +204,22 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
     f.max_mat = std::max({(size_t)f.nz * f.nz, (size_t)f.half * f.w, (size_t)f.w * f.w, (size_t)f.w * f.n_out});
     f.step_floats = o;
     p->off_flow = take(f.step_floats * 4 * c.f_depth);
+    // training stash and flat gradient layout of the flow parameter update (train.py:403-415)
+    FlowStash& t = p->fstash;
+    size_t so = 0;
+    auto ts = [&](size_t n) { size_t r = so; so += n; return r; };
+    t.y = ts(f.nz); t.u1 = ts(f.half); t.a1 = ts(f.w); t.a2 = ts(f.w); t.h = ts(f.n_out);
+    t.gu = ts(f.nz); t.gp1 = ts(f.w); t.gp2 = ts(f.w); t.gp3 = ts(f.n_out); t.gx = ts(f.nz);
+    t.gl0 = ts(f.nz); t.gl1 = ts(f.w); t.gl2 = ts(f.w); t.gl3 = ts(f.n_out);
+    t.layer_floats = so;
+    p->off_fstash = take(so * 4 * (size_t)B * c.f_depth);
+    FlowGradLayout& gl = p->fgrad;
+    const size_t sizes[LSNF_FLOW_PTRS_PER_STEP] = {
+        (size_t)f.nz, (size_t)f.nz, (size_t)f.nz * f.nz, (size_t)f.half * f.w, (size_t)f.w, (size_t)f.w,
+        (size_t)f.w * f.w, (size_t)f.w, (size_t)f.w, (size_t)f.w * f.n_out, (size_t)f.n_out, (size_t)f.n_out};
+    size_t go = 0;
+    for (int i = 0; i < LSNF_FLOW_PTRS_PER_STEP; ++i) { gl.off[i] = go; gl.size[i] = sizes[i]; go += (sizes[i] + 3) / 4 * 4; }
+    gl.step_floats = go;
   }
 
   if (L > 0) {
@@ -595,6 +611,40 @@ extern "C" int lsnf_flow_inverse(lsnf_plan* plan, const float* eps, float* z, fl
   if (!eps || !z) return fail(LSNF_ERR_INVALID, "null argument");
   if (!plan->have_winv) return fail(LSNF_ERR_STATE, "flow weights were packed without w_inverse");
   return launch_flow_inverse(plan, eps, z, neg_objective, (cudaStream_t)stream);
+}
+
+extern "C" size_t lsnf_flow_grad_floats(const lsnf_plan* plan) {
+  return plan ? plan->fgrad.step_floats * (size_t)plan->cfg.f_depth : 0;
+}
+
+extern "C" int lsnf_flow_grad_layout(const lsnf_plan* plan, int64_t* offsets, int64_t* sizes) {
+  if (!plan || !offsets || !sizes) return fail(LSNF_ERR_INVALID, "null argument");
+  for (int L = 0; L < plan->cfg.f_depth; ++L)
+    for (int i = 0; i < LSNF_FLOW_PTRS_PER_STEP; ++i) {
+      offsets[L * LSNF_FLOW_PTRS_PER_STEP + i] = (int64_t)(L * plan->fgrad.step_floats + plan->fgrad.off[i]);
+      sizes[L * LSNF_FLOW_PTRS_PER_STEP + i] = (int64_t)plan->fgrad.size[i];
+    }
+  return LSNF_OK;
+}
+
+extern "C" int lsnf_flow_param_grads(lsnf_plan* plan, const float* z, int32_t global_batch, float* grads, float* loss,
+                                     lsnf_stream stream) {
+  int rc = need(plan, false, true);
+  if (rc) return rc;
+  if (!z || !grads || global_batch <= 0) return fail(LSNF_ERR_INVALID, "bad argument");
+  if (plan->cfg.f_permutation == 2 && !plan->have_winv)
+    return fail(LSNF_ERR_STATE, "flow weights were packed without w_inverse (needed for d log|det W| / dW = W^-T)");
+  return launch_flow_param_grads(plan, z, 1.f / (float)global_batch, grads, loss, (cudaStream_t)stream);
+}
+
+extern "C" int lsnf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, const int64_t* sizes, const int32_t* grad_kk,
+                              const int32_t* grad_inner, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int64_t step, const float* grad_scale, lsnf_stream stream) {
+  if (n_tensors <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !sizes || step <= 0)
+    return fail(LSNF_ERR_INVALID, "bad argument");
+  return launch_adam(n_tensors, params, grads, exp_avg, exp_avg_sq, sizes, grad_kk, grad_inner, lr, beta1, beta2, eps,
+                     weight_decay, step, grad_scale, (cudaStream_t)stream);
 }
 
 extern "C" int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int32_t to_unit_range,

@@ -208,6 +208,30 @@ class Plan:
                                                    _stream(self.device)), "lsnf_sample_prior")
         return (x, z) if want_z else x
 
+    # ---- flow parameter update (train.py:403-415) ----------------------------------------------------
+    def flow_grad_layout(self):
+        """[(offset, size)] of every flow parameter gradient inside the flat buffer, step-major, in the order of
+        ``_FLOW_PARAM_ORDER`` (include/lsnf.h: lsnf_flow_grad_layout)."""
+        n = self.f_depth * _cabi.FLOW_PTRS_PER_STEP
+        off, size = (C.c_int64 * n)(), (C.c_int64 * n)()
+        _cabi.check(self.lib.lsnf_flow_grad_layout(self.handle, off, size), "lsnf_flow_grad_layout")
+        return [(int(off[i]), int(size[i])) for i in range(n)]
+
+    def flow_param_grads(self, z: torch.Tensor, global_batch: int, flat: Optional[torch.Tensor] = None):
+        """Gradients of loss_f = -(1/global_batch) sum_b log p(z_b) w.r.t. every flow parameter, into one flat
+        fp32 buffer (returned with this rank's share of loss_f as a 0-d tensor).  ``ensure_flow(netF,
+        need_inverse=True)`` must have packed the current parameters."""
+        _check_tensor(z, "z", self.device, (self.batch, self.nz))
+        n = int(self.lib.lsnf_flow_grad_floats(self.handle))
+        if flat is None:
+            flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        _check_tensor(flat, "flat gradient buffer", self.device, (n,))
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.lsnf_flow_param_grads(self.handle, z.data_ptr(), int(global_batch), flat.data_ptr(),
+                                                       loss.data_ptr(), _stream(self.device)), "lsnf_flow_param_grads")
+        return flat, loss
+
     def langevin_update(self, z, grad_g, grad_f, step_size, eps=None, with_noise=True, seed=0, sample_offset=0,
                         step=0, want_norms=True):
         for t, n in ((z, "z"), (grad_g, "grad_g"), (grad_f, "grad_f")):

@@ -24,6 +24,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:tapg
 echo "ncu full rc=$?"; tail -2 gpurun_out/ncu_full.log
 python tools/ncu_summarize.py gpurun_out/prof_r2_dominant.ncu-rep gpurun_out/r2_ncu_full_tapgemm_pair.json --dominant cifar10 100 1,2,5,6
 FLOW=1 timeout 300 python tools/prof_stage.py 0 > gpurun_out/plain_prof_flow.log 2>&1 &&
-FLOW=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:flow_ -c 2 -f -o gpurun_out/prof_r2_flow python tools/prof_stage.py 0 > gpurun_out/ncu_flow.log 2>&1
+FLOW=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:flow_forward_kernel|flow_inverse_kernel" -c 2 -f -o gpurun_out/prof_r2_flow python tools/prof_stage.py 0 > gpurun_out/ncu_flow.log 2>&1
 echo "ncu flow rc=$?"
 python tools/ncu_summarize.py gpurun_out/prof_r2_flow.ncu-rep gpurun_out/r2_ncu_full_flow.json
