@@ -12,6 +12,7 @@
  *   lsnf_langevin_update     <- z update + noise + diagnostics            train.py:324-329
  *   lsnf_langevin_run        <- sample_langevin_post_z_with_flow          train.py:307-335, :602-634
  *   lsnf_sample_prior        <- sample_x(): eps -> F^-1 -> G -> [0,1]     train.py:565-576, :433-437, :472-478
+ *   lsnf_generator_param_grads <- loss_g = mse(G(z_k), x) / B; loss_g.backward()  train.py:390-394
  *   lsnf_flow_param_grads    <- loss_f = -ll.mean(); loss_f.backward()    train.py:403-411, model.py:182
  *   lsnf_adam_step           <- optG.step() / optF.step() (torch.optim.Adam) train.py:294-295, :398, :415
  *   lsnf_pack_*              <- parameters of _netG / _netF               model.py:48-157, :460-498
@@ -84,7 +85,9 @@ typedef struct lsnf_config {
                             per K step: arithmetic not narrower than the reference's fp32.  1 = explicit opt-in to a
                             single fp16 pass (11-bit significands, gradient good to ~2e-4): a reduced-precision mode,
                             measured margins in DESIGN.md section 4.1 */
-  int32_t reserved[4];
+  int32_t train;         /* != 0: the workspace also holds the buffers of lsnf_generator_param_grads (transposed
+                            operands and split-K partials of the weight-gradient GEMMs); 0 for inference-only plans */
+  int32_t reserved[3];
 } lsnf_config;
 
 /* number of per-step flow parameter pointers expected by lsnf_pack_flow_weights, in this order:
@@ -152,6 +155,17 @@ int lsnf_langevin_run(lsnf_plan* plan, const float* z0, const float* x, int32_t 
  * weights packed with w_inverse. */
 int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int32_t to_unit_range, lsnf_stream stream);
 /* ---- parameter updates (training mode) ---------------------------------------------------------------- */
+/* Generator parameter gradients of loss_g = (1 / global_batch) * sum (G(z) - x)^2 over this plan's batch
+ * (train.py:390-394): z [B,nz] (the inferred latents z_k), x [B,nc,H,W].  Needs a plan created with
+ * lsnf_config.train != 0.  grads: device buffer of lsnf_generator_grad_floats() floats; layer l's weight gradient
+ * occupies [offsets[2l], +sizes[2l]) in the parameter's own [C_in,C_out,k,k] layout and its bias gradient
+ * [offsets[2l+1], +sizes[2l+1]) (lsnf_generator_grad_layout).  With several ranks each passes its shard and the GLOBAL
+ * batch size; the buffers are then summed (one all-reduce).  loss (nullable, device float): this rank's share of
+ * loss_g.  Runs the forward pass, the data-gradient chain and one weight-gradient tap-GEMM per layer; deterministic. */
+size_t lsnf_generator_grad_floats(const lsnf_plan* plan);
+int lsnf_generator_grad_layout(const lsnf_plan* plan, int64_t* offsets, int64_t* sizes);
+int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const float* x, int32_t global_batch, float* grads,
+                               float* loss, lsnf_stream stream);
 /* Flow parameter gradients of loss_f = -(1 / global_batch) * sum_b ll_b(z_b) over this plan's batch z [B,nz]
  * (train.py:403-411; ll_b = log p(z_b) of lsnf_flow_forward).  grads: device buffer of lsnf_flow_grad_floats()
  * floats, ZERO-INITIALISED by the caller once (alignment padding is never written); tensor (step, i) -- i in the order

@@ -22,7 +22,7 @@ class Config(C.Structure):
     _fields_ = [("arch", C.c_int32), ("batch", C.c_int32), ("nz", C.c_int32), ("ngf", C.c_int32), ("nc", C.c_int32),
                 ("f_depth", C.c_int32), ("f_width", C.c_int32), ("f_permutation", C.c_int32),
                 ("f_coupling", C.c_int32), ("leak", C.c_float), ("gemm_impl", C.c_int32),
-                ("bwd_passes", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("bwd_passes", C.c_int32), ("train", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Tap(C.Structure):
@@ -73,6 +73,10 @@ EXPORTS = {
     "lsnf_langevin_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsnf_sample_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "lsnf_generator_grad_floats": (C.c_size_t, [C.c_void_p]),
+    "lsnf_generator_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lsnf_generator_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
     "lsnf_flow_grad_floats": (C.c_size_t, [C.c_void_p]),
     "lsnf_flow_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lsnf_flow_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

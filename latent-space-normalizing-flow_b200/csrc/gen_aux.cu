@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) last_fused_kernel(const float* __restrict
   }
 }
 
-int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s) {
+int launch_last_fused(const lsnf_plan* plan, const float* x, float seed_scale, cudaStream_t s) {
   const auto& y = plan->layers[plan->n_layers - 1];
   const int n_pad = plan->dlast_pad;
   const int TC = std::min(32, y.hin), TR = std::min(n_pad <= 32 ? 8 : 4, y.hin);
@@ -396,11 +396,11 @@ int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaSt
   if (y.k == 3 && y.s == 1)
     last_fused_kernel<3, 1><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
                                                                       plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      sigma_seed_scale(sigma), one, !one);
+                                                                      seed_scale, one, !one);
   else
     last_fused_kernel<4, 2><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
                                                                       plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      sigma_seed_scale(sigma), one, !one);
+                                                                      seed_scale, one, !one);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;
 }

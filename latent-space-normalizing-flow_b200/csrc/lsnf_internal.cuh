@@ -25,7 +25,9 @@ enum Epilogue : int32_t {
 };
 
 struct TapDev {
-  int16_t dy, dx, plane, pad_;
+  int16_t dy, dx, plane;
+  int16_t bsh;   // column shift of the B operand box (weight-gradient stages: the tap's offset in the flattened,
+                 // zero-haloed position axis); 0 everywhere else
   int32_t brow;
 };
 
@@ -62,7 +64,9 @@ struct StageDev {
   int64_t rows_total;                 // B*Hg*Wg (row stride of one split in EPI_PARTIAL)
   float* sk_slots;                    // stream-K: one fp32 partial accumulator [128][256] per CTA of the pair grid
   int32_t* sk_flags;                  // stream-K: one flag per (CTA, epilogue warp), 0 = empty, 1 = partial ready
-  int32_t sk_enable, pad2_;           // stream-K on/off for this launch
+  int32_t sk_enable;                  // stream-K on/off for this launch
+  int32_t wgrad;                      // weight-gradient stage (train.py:394): rows = C_in, columns = C_out, K = the
+                                      // flattened zero-haloed positions; every blockIdx.z slice is ONE tap (x split)
   int32_t out_tma, nst;               // hi|lo output written by TMA tensor stores (1 up2 forward, 2 first layer,
                                       // 3 plain gradient, 4 phase-split gradient; 0 = per-thread stores); ring depth
                                       // of this launch (1-CTA kernel)
@@ -108,6 +112,48 @@ struct FlowGradLayout {
   size_t step_floats;
 };
 
+// arguments of the weight-gradient helper kernels (wgrad.cu)
+struct TransArgs {
+  const uint16_t* src;
+  uint16_t* dst;
+  int P, B, H, W, C;
+  long long s_plane, s_b, s_h, s_w;   // source strides (elements)
+  int src_fp16, src_single;           // halves are fp16 (else bf16); the lo half is absent
+  int Hp, Wp, halo;
+  long long Kp;                       // columns of one half of a destination row
+  int c_rows;                         // destination rows per plane (>= C)
+};
+
+struct FinalizeArgs {
+  const float* part;
+  float* out;
+  long long s_tap, s_split, s_ci;
+  int ksplit, kk, C_in, C_out;
+  float scale;
+};
+
+struct RowSumArgs {
+  const uint16_t* src;
+  float* out;
+  long long Kp;
+  int nsel, C;
+  float scale;
+  int sel[64];
+};
+
+// One layer of the generator parameter update: transposed operand buffers, the weight-gradient tap-GEMM and where
+// its results go in the flat gradient buffer.
+struct WgradLayer {
+  StageHost st;
+  TransArgs ta, tg;          // act_{l-1} -> aT, gpre_l (or the im2col seed) -> gT
+  size_t off_aT = 0, off_gT = 0, off_part = 0;
+  int a_rows = 0, g_rows = 0, planes = 1, ntaps = 1, kk = 1, ksplit = 1;
+  long long Kp = 0;
+  size_t grad_w_off = 0, grad_b_off = 0;   // floats, in the flat gradient buffer
+  FinalizeArgs fin;
+  RowSumArgs rs;
+};
+
 }  // namespace lsnf
 
 struct lsnf_plan {
@@ -119,6 +165,8 @@ struct lsnf_plan {
   struct Layer { int ci, co, k, s, p, hin, hout; } layers[8];
   std::vector<lsnf::StageHost> stages;  // forward stages 0..L-1, then data-gradient stages L-1..0
   lsnf::FlowLayout fl;
+  std::vector<lsnf::WgradLayer> wg;     // training plans only (cfg.train)
+  size_t gen_grad_floats = 0;
   lsnf::FlowStash fstash;
   lsnf::FlowGradLayout fgrad;
   size_t off_fstash = 0, off_fgrad = 0, off_floss = 0;
@@ -191,7 +239,11 @@ int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
 int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);
 int launch_last_gather(const lsnf_plan* plan, float* out, int to_unit_range, cudaStream_t s);
 int launch_recon_grad_im2col(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
-int launch_last_fused(const lsnf_plan* plan, const float* x, float sigma, cudaStream_t s);
+int launch_last_fused(const lsnf_plan* plan, const float* x, float seed_scale, cudaStream_t s);
+int launch_transpose_hl(const TransArgs& a, cudaStream_t s);
+int launch_wgrad_finalize(const FinalizeArgs& a, cudaStream_t s);
+int launch_bias_rowsum(const RowSumArgs& a, cudaStream_t s);
+int launch_mse_sum(const float* xh, const float* x, long long n, float scale, float* out, cudaStream_t s);
 int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, float scale, cudaStream_t s);
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                      const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,

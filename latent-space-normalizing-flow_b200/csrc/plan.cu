@@ -402,6 +402,116 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
     p->stages[2 * L - 1].out_off = p->off_partial;
     p->stages[2 * L - 1].info.out_offset = p->off_partial;
   }
+  // ---- generator parameter update (train.py:390-394): transposed operands + weight-gradient tap-GEMMs ----
+  if (L > 0 && c.train) {
+    p->wg.resize(L);
+    size_t goff = 0;
+    for (int l = 0; l < L; ++l) {
+      const auto& y = p->layers[l];
+      WgradLayer& w = p->wg[l];
+      const bool first = (l == 0), last = (l == L - 1);
+      const int kk = y.k * y.k;
+      const bool single = c.bwd_passes == 1;   // gradient tensors hold fp16 hi halves only
+      w.kk = kk;
+      int n_cols, hp, wp, halo, block_n;
+      TransArgs& ta = w.ta;
+      TransArgs& tg = w.tg;
+      memset(&ta, 0, sizeof(ta)); memset(&tg, 0, sizeof(tg));
+      if (first) {
+        // dW0[ci][(tap, co)] = sum_b z[b][ci] * gpre_0[b][tap][co]
+        w.a_rows = (int)align_up(c.nz, 128); hp = wp = 1; halo = 0;
+        w.Kp = (long long)align_up(B, BLOCK_K);
+        w.planes = 1; w.g_rows = kk * y.co; w.ntaps = 1; n_cols = kk * y.co; block_n = pick_block_n(n_cols);
+        ta.P = 1; ta.B = B; ta.H = ta.W = 1; ta.C = p->kp; ta.s_b = 2 * p->kp; ta.src_fp16 = 1; ta.c_rows = w.a_rows;
+        tg.P = kk; tg.B = B; tg.H = tg.W = 1; tg.C = y.co; tg.s_plane = 2 * y.co; tg.s_b = (long long)kk * 2 * y.co;
+        tg.c_rows = y.co;
+      } else if (last) {
+        // dW[ci][(tap, c)] = sum_pos act[pos][ci] * im2col_seed[pos][(tap, c)]   (the seed already holds the taps)
+        w.a_rows = y.ci; hp = wp = y.hin; halo = 0;
+        w.Kp = (long long)align_up((size_t)B * y.hin * y.hin, BLOCK_K);
+        w.planes = 1; w.g_rows = BLOCK_K; w.ntaps = 1; n_cols = BLOCK_K; block_n = 64;
+        ta.P = 1; ta.B = B; ta.H = ta.W = y.hin; ta.C = y.ci; ta.s_w = 2 * y.ci; ta.s_h = (long long)y.hin * ta.s_w;
+        ta.s_b = (long long)y.hin * ta.s_h; ta.src_fp16 = 1; ta.c_rows = y.ci;
+        tg.P = 1; tg.B = B; tg.H = tg.W = y.hin; tg.C = BLOCK_K; tg.s_w = 2 * BLOCK_K; tg.s_h = (long long)y.hin * tg.s_w;
+        tg.s_b = (long long)y.hin * tg.s_h; tg.c_rows = BLOCK_K;
+      } else {
+        // k4/s2/p1: per tap, dW[ci][co] = sum_pos act[pos][ci] * gpre[plane_tap][pos + (dy, dx)][co]
+        w.a_rows = y.ci; hp = wp = y.hin + 2; halo = 1;
+        w.Kp = (long long)align_up((size_t)B * hp * wp, BLOCK_K);
+        w.planes = 4; w.g_rows = y.co; w.ntaps = 16; n_cols = y.co; block_n = pick_block_n(y.co);
+        ta.P = 1; ta.B = B; ta.H = ta.W = y.hin; ta.C = y.ci; ta.s_w = 2 * y.ci; ta.s_h = (long long)y.hin * ta.s_w;
+        ta.s_b = (long long)y.hin * ta.s_h; ta.src_fp16 = 1; ta.c_rows = y.ci;
+        tg.P = 4; tg.B = B; tg.H = tg.W = y.hin; tg.C = y.co; tg.s_w = 2 * y.co; tg.s_h = (long long)y.hin * tg.s_w;
+        tg.s_b = (long long)y.hin * tg.s_h; tg.s_plane = (long long)B * tg.s_b; tg.c_rows = y.co;
+      }
+      ta.Hp = tg.Hp = hp; ta.Wp = tg.Wp = wp; ta.halo = tg.halo = halo; ta.Kp = tg.Kp = w.Kp;
+      tg.src_fp16 = single ? 1 : 0; tg.src_single = single ? 1 : 0;
+      w.off_aT = take((size_t)w.a_rows * 2 * w.Kp * 2);
+      w.off_gT = take((size_t)w.planes * w.g_rows * 2 * w.Kp * 2);
+      // the tap-GEMM: rows = C_in, columns = C_out (or (tap, co) / the 64 seed columns), K = flattened positions
+      StageHost& st = w.st;
+      lsnf_stage_info& I = st.info;
+      memset(&I, 0, sizeof(I));
+      st.layer = l; st.kind = 2; st.k = y.k; st.s = y.s; st.p = y.p; st.ci = y.ci; st.co = y.co;
+      st.first = first; st.last = last;
+      I.kind = 2; I.layer = l; I.grid_h = 1; I.grid_w = w.a_rows; I.box_b = 1; I.box_h = 1; I.box_w = BLOCK_M;
+      I.k_per_tap = (int)w.Kp; I.n_valid = n_cols; I.block_n = block_n; I.n_pad = (int)align_up(n_cols, block_n);
+      I.n_phases = 1; I.n_taps[0] = w.ntaps; I.out_mul = 1; I.out_channels = I.n_pad; I.epilogue = EPI_PARTIAL;
+      I.a_planes = 1; I.a_h = 1; I.a_w = w.a_rows; I.b_k = (int)w.Kp; I.b_rows = w.planes * w.g_rows;
+      I.operand_fp16 = 0; I.passes = 3;
+      const int kblocks = (int)(w.Kp / BLOCK_K);
+      const int tiles = ((w.a_rows + BLOCK_M - 1) / BLOCK_M) * (I.n_pad / block_n) * w.ntaps;
+      int want = std::max(1, (2 * 148 + tiles - 1) / tiles);
+      want = std::min(want, std::max(1, kblocks / 4));          // at least four K blocks per split
+      int per = (kblocks + want - 1) / want;
+      w.ksplit = (kblocks + per - 1) / per;
+      I.k_splits = w.ksplit;
+      for (int t = 0; t < w.ntaps; ++t) I.taps[0][t] = {0, 0, 0, 0};
+      I.flops = 2LL * w.a_rows * (long long)n_cols * w.Kp * w.ntaps;
+      st.a_off = w.off_aT; st.b_off = w.off_gT;
+      w.off_part = take((size_t)w.ntaps * w.ksplit * w.a_rows * I.n_pad * 4);
+      st.out_off = w.off_part;
+      I.a_offset = st.a_off; I.b_offset = st.b_off; I.out_offset = st.out_off;
+      fill_dev(p, st);
+      StageDev& d = st.dev;
+      d.B = 1; d.tiles_b = 1; d.tiles_h = 1; d.tiles_w = (w.a_rows + BLOCK_M - 1) / BLOCK_M;
+      d.rows_total = w.a_rows; d.wgrad = 1; d.it_per_split = per;
+      if (!first && !last) {
+        lsnf_tap tp[16];
+        up2_bwd_taps(y.co, tp);   // plane and (dy, dx) of every tap; brow = plane * C_out in the transposed gradient
+        for (int t = 0; t < 16; ++t) {
+          d.ph[0].taps[t].dy = 0; d.ph[0].taps[t].dx = 0; d.ph[0].taps[t].plane = 0;
+          d.ph[0].taps[t].bsh = (int16_t)(tp[t].dy * wp + tp[t].dx);
+          d.ph[0].taps[t].brow = tp[t].plane * y.co;
+        }
+      }
+      // results: dW in the parameter's own layout, then db
+      w.grad_w_off = goff; goff += align_up((size_t)y.ci * y.co * kk, 4);
+      w.grad_b_off = goff; goff += align_up((size_t)y.co, 4);
+      FinalizeArgs& f = w.fin;
+      memset(&f, 0, sizeof(f));
+      f.ksplit = w.ksplit; f.kk = kk; f.C_in = y.ci; f.C_out = y.co;
+      if (first) { f.s_tap = y.co; f.s_split = 0; f.s_ci = I.n_pad; f.ksplit = 1; }
+      else if (last) { f.s_tap = y.co; f.s_split = (long long)w.a_rows * I.n_pad; f.s_ci = I.n_pad; }
+      else { f.s_tap = (long long)w.ksplit * w.a_rows * I.n_pad; f.s_split = (long long)w.a_rows * I.n_pad; f.s_ci = I.n_pad; }
+      RowSumArgs& r = w.rs;
+      memset(&r, 0, sizeof(r));
+      r.Kp = w.Kp; r.C = y.co;
+      if (first) { r.nsel = kk; for (int t = 0; t < kk; ++t) r.sel[t] = t * y.co; }
+      else if (last) {
+        // every output pixel is produced by exactly one of these taps (oy = iy*s - p + ky covers each oy once)
+        r.nsel = 0;
+        for (int ky = 0; ky < y.k; ++ky)
+          for (int kx = 0; kx < y.k; ++kx) {
+            const bool once_y = y.s == 1 ? ky == y.p : (ky == 1 || ky == 2);
+            const bool once_x = y.s == 1 ? kx == y.p : (kx == 1 || kx == 2);
+            if (once_y && once_x) r.sel[r.nsel++] = (ky * y.k + kx) * y.co;
+          }
+      } else { r.nsel = 4; for (int q = 0; q < 4; ++q) r.sel[q] = q * y.co; }
+      if (first && w.ksplit != 1) { /* K = batch only: never split */ }
+    }
+    p->gen_grad_floats = goff;
+  }
   p->ws_bytes = off;
   *out = p;
   return LSNF_OK;
@@ -486,6 +596,22 @@ extern "C" int lsnf_plan_bind(lsnf_plan* plan, void* workspace, size_t bytes) {
       int rc = tc_encode_maps(plan, st);
       if (rc) return rc;
     }
+  }
+  for (auto& w : plan->wg) {
+    StageHost& st = w.st;
+    StageDev& d = st.dev;
+    st.num_sms = plan->num_sms;
+    d.a = (const __nv_bfloat16*)(plan->ws + st.a_off);
+    d.b = (const __nv_bfloat16*)(plan->ws + st.b_off);
+    d.out = plan->ws + st.out_off;
+    d.bias = nullptr; d.descale = nullptr; d.mbits = nullptr;
+    d.sk_slots = nullptr; d.sk_flags = nullptr;
+    int rc = tc_encode_maps(plan, st);
+    if (rc) return rc;
+    w.ta.dst = (uint16_t*)(plan->ws + w.off_aT);
+    w.tg.dst = (uint16_t*)(plan->ws + w.off_gT);
+    w.fin.part = (const float*)(plan->ws + w.off_part);
+    w.rs.src = (const uint16_t*)(plan->ws + w.off_gT);
   }
   if (!plan->side) {
     LSNF_CUDA(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
@@ -611,6 +737,57 @@ extern "C" int lsnf_flow_inverse(lsnf_plan* plan, const float* eps, float* z, fl
   if (!eps || !z) return fail(LSNF_ERR_INVALID, "null argument");
   if (!plan->have_winv) return fail(LSNF_ERR_STATE, "flow weights were packed without w_inverse");
   return launch_flow_inverse(plan, eps, z, neg_objective, (cudaStream_t)stream);
+}
+
+extern "C" size_t lsnf_generator_grad_floats(const lsnf_plan* plan) { return plan ? plan->gen_grad_floats : 0; }
+
+extern "C" int lsnf_generator_grad_layout(const lsnf_plan* plan, int64_t* offsets, int64_t* sizes) {
+  if (!plan || !offsets || !sizes) return fail(LSNF_ERR_INVALID, "null argument");
+  if (plan->wg.empty()) return fail(LSNF_ERR_STATE, "plan was created without lsnf_config.train");
+  for (int l = 0; l < plan->n_layers; ++l) {
+    const auto& y = plan->layers[l];
+    offsets[2 * l] = (int64_t)plan->wg[l].grad_w_off; sizes[2 * l] = (int64_t)y.ci * y.co * y.k * y.k;
+    offsets[2 * l + 1] = (int64_t)plan->wg[l].grad_b_off; sizes[2 * l + 1] = y.co;
+  }
+  return LSNF_OK;
+}
+
+extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const float* x, int32_t global_batch,
+                                          float* grads, float* loss, lsnf_stream stream) {
+  int rc = need(plan, true, false);
+  if (rc) return rc;
+  if (plan->wg.empty()) return fail(LSNF_ERR_STATE, "plan was created without lsnf_config.train");
+  if (plan->cfg.gemm_impl != LSNF_GEMM_TCGEN05) return fail(LSNF_ERR_UNSUPPORTED, "weight gradients need the tcgen05 path");
+  if (!z || !x || !grads || global_batch <= 0) return fail(LSNF_ERR_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const lsnf_config& c = plan->cfg;
+  const int L = plan->n_layers;
+  // x_hat = G(z_k) (train.py:392) and loss_g = mse_sum / B (train.py:393)
+  if ((rc = gen_forward(plan, z, nullptr, s, true))) return rc;
+  const long long npix = (long long)c.batch * c.nc * plan->img * plan->img;
+  if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch, loss, s)))
+    return rc;
+  // backward through the generator: seed (x_hat - x)(1 - x_hat^2) unscaled; the factor 2 / B of the loss is applied
+  // in fp32 when the gradients are finalized.  The first layer's data gradient is not needed.
+  if ((rc = launch_last_fused(plan, x, 1.f, s))) return rc;
+  for (int i = L; i < 2 * L - 1; ++i)
+    if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+  const float scale = 2.f / (float)global_batch;
+  for (int l = L - 1; l >= 0; --l) {
+    WgradLayer& w = plan->wg[l];
+    TransArgs ta = w.ta, tg = w.tg;
+    ta.src = (const uint16_t*)(plan->ws + (l == 0 ? plan->off_zhl : plan->off_act[l - 1]));
+    tg.src = (const uint16_t*)(plan->ws + (l == L - 1 ? plan->off_im2col : plan->off_gpre[l]));
+    if ((rc = launch_transpose_hl(ta, s)) || (rc = launch_transpose_hl(tg, s))) return rc;
+    if ((rc = launch_tapgemm_tc(w.st, s))) return rc;
+    FinalizeArgs f = w.fin;
+    f.out = grads + w.grad_w_off; f.scale = scale;
+    if ((rc = launch_wgrad_finalize(f, s))) return rc;
+    RowSumArgs r = w.rs;
+    r.out = grads + w.grad_b_off; r.scale = scale;
+    if ((rc = launch_bias_rowsum(r, s))) return rc;
+  }
+  return LSNF_OK;
 }
 
 extern "C" size_t lsnf_flow_grad_floats(const lsnf_plan* plan) {
@@ -744,7 +921,7 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
       if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
       tr.mark(("forward layer " + std::to_string(l)).c_str());
     }
-    if ((rc = launch_last_fused(plan, x, sigma, s))) return rc;
+    if ((rc = launch_last_fused(plan, x, sigma_seed_scale(sigma), s))) return rc;
     tr.mark("gather + tanh + recon grad + im2col");
     for (int i = plan->n_layers; i < 2 * plan->n_layers; ++i) {
       if ((rc = run_stage(plan, plan->stages[i], s))) return rc;

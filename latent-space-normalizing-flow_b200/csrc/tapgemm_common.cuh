@@ -21,7 +21,7 @@ __device__ __forceinline__ RowCtx tile_row(const StageDev& st, int mtile, int r)
   rc.n = w0 + r % st.bW;
   rc.m = h0 + (r / st.bW) % st.bH;
   rc.b = b0 + r / (st.bW * st.bH);
-  rc.valid = rc.b < st.B;
+  rc.valid = rc.b < st.B && rc.n < st.Wg;   // ragged batch; rows of a partial tile (weight-gradient stages)
   return rc;
 }
 
@@ -107,7 +107,7 @@ __device__ __forceinline__ void get_tap(const StageDev& st, int phase, int t, in
     dy = t / st.tap_gen; dx = t % st.tap_gen; plane = 0; brow = 0; bcol = t * st.Ka;
   } else {
     const TapDev& tp = st.ph[phase].taps[t];
-    dy = tp.dy; dx = tp.dx; plane = tp.plane; brow = tp.brow; bcol = 0;
+    dy = tp.dy; dx = tp.dx; plane = tp.plane; brow = tp.brow; bcol = tp.bsh;
   }
 }
 

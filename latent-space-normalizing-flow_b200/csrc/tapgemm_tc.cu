@@ -350,9 +350,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtile = blockIdx.x, n0 = blockIdx.y * BN;
-  const int phase = blockIdx.z / st.ksplit, split = blockIdx.z % st.ksplit;
+  const int zphase = blockIdx.z / st.ksplit, split = blockIdx.z % st.ksplit;
+  const bool wg = st.wgrad != 0;                 // weight gradient: slice zphase is tap zphase of phase 0, alone
+  const int phase = wg ? 0 : zphase, tap0 = wg ? zphase : 0;
   const int kblocks = st.Ka / BLOCK_K;
-  const int total = st.ph[phase].ntaps * kblocks;
+  const int total = (wg ? 1 : st.ph[phase].ntaps) * kblocks;
   const int it0 = split * st.it_per_split, it1 = min(total, it0 + st.it_per_split);
 
   if (warp == 0 && lane == 0) {
@@ -384,6 +386,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tile_origin(st, mtile, b0, h0, w0);
       uint32_t s = 0, par = 0, sa = tiles;
       int tp = it0 / kblocks, kc = (it0 - tp * kblocks) * BLOCK_K;
+      tp += tap0;
       int dy = 0, dx = 0, plane = 0, brow = 0, bcol = 0;
       if (it1 > it0) get_tap(st, phase, tp, dy, dx, plane, brow, bcol);
       for (int it = it0; it < it1; ++it) {
@@ -448,7 +451,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         done = true;
       }
     }
-    if (!done) tc_epilogue<BN>(st, mtile, n0, phase, split, warp, lane, tmem_base, tmem_full_bar, 0u, it1 > it0);
+    // weight-gradient slices land at [tap][split][C_in][C_out]: blockIdx.z IS tap * ksplit + split
+    if (!done) tc_epilogue<BN>(st, mtile, n0, phase, wg ? (int)blockIdx.z : split, warp, lane, tmem_base, tmem_full_bar,
+                               0u, it1 > it0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -964,7 +969,7 @@ static bool use_pair(const StageHost& sh) {
   const StageDev& d = sh.dev;
   const int mtiles = d.tiles_b * d.tiles_h * d.tiles_w;
   const int total = d.ph[0].ntaps * (d.Ka / BLOCK_K);
-  return pair_enabled() && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 && total >= 3 &&
+  return pair_enabled() && !d.wgrad && d.block_n == 256 && d.n_pad % 256 == 0 && d.ksplit == 1 && total >= 3 &&
          (mtiles >= 2 || total >= 8);
 }
 
@@ -1099,7 +1104,7 @@ static int launch_bn(const StageHost& sh, cudaStream_t s) {
   StageDev st = sh.dev;
   const RingGeom g = ring_geometry(st);
   st.nst = g.nst;
-  dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, st.nphase * st.ksplit);
+  dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, (st.wgrad ? st.ph[0].ntaps : st.nphase) * st.ksplit);
   tapgemm_tc_kernel<BN><<<grid, TC_THREADS, g.smem, s>>>(sh.tmA, sh.tmB, sh.tmO, st);
   LSNF_CUDA(cudaGetLastError());
   return LSNF_OK;

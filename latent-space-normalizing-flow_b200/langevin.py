@@ -33,16 +33,18 @@ def make_args(**overrides) -> AttrDict:
     return a
 
 
-def langevin_plan(netG: _netG, netF: _netF, batch: int, device, bwd_passes: Optional[int] = None):
+def langevin_plan(netG: _netG, netF: _netF, batch: int, device, bwd_passes: Optional[int] = None, train: bool = False):
+    """The plan (workspace, packed parameters, CUDA graphs) of one (netG, netF, batch) configuration; ``train=True``
+    adds the buffers of the generator parameter update so that one plan serves a whole training iteration."""
     return get_plan(arch=netG.dataset, batch=batch, nz=netG.nz, ngf=netG.ngf, nc=netG.nc, f_depth=netF.f_depth,
                     f_width=netF.f_width, f_permutation=netF.f_permutation, f_coupling=netF.f_coupling,
-                    leak=netG.leak, device=device, gemm_impl=netG.gemm_impl, bwd_passes=bwd_passes)
+                    leak=netG.leak, device=device, gemm_impl=netG.gemm_impl, bwd_passes=bwd_passes, train=train)
 
 
 def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbose: bool = False, *,
                                      eps: Optional[torch.Tensor] = None, steps: Optional[int] = None,
                                      with_noise: Optional[bool] = None, seed: Optional[int] = None,
-                                     sample_offset: int = 0, bwd_passes: Optional[int] = None):
+                                     sample_offset: int = 0, bwd_passes: Optional[int] = None, train: bool = False):
     """z [B,nz,1,1], x [B,nc,H,W] -> (z_k [B,nz,1,1], mean_b|grad_g|, mean_b|grad_f|) as train.py:335 returns them.
 
     ``args`` supplies g_l_steps, g_l_step_size, g_l_with_noise, g_llhd_sigma (train.py:311-326).  ``eps``
@@ -74,7 +76,7 @@ def sample_langevin_post_z_with_flow(z, x, netG: _netG, netF: _netF, args, verbo
     noisy = noise or eps is not None
     if bwd_passes is None:
         bwd_passes = default_bwd_passes(noisy_chain=noisy)
-    plan = langevin_plan(netG, netF, B, z2.device, bwd_passes)
+    plan = langevin_plan(netG, netF, B, z2.device, bwd_passes, train=train)
     plan.ensure_generator(netG)
     plan.ensure_flow(netF)
     out, norms = plan.langevin_run(z2, xx, T, s, sigma, with_noise=noise, eps=e, seed=seed,

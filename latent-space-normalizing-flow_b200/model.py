@@ -76,9 +76,10 @@ class _netG(nn.Module):
         self.gen = nn.Sequential(*mods)
         self.gemm_impl = 0
 
-    def _plan(self, batch, device):
+    def _plan(self, batch, device, train=False):
         return get_plan(arch=self.dataset, batch=batch, nz=self.nz, ngf=self.ngf, nc=self.nc, f_depth=1, f_width=4,
-                        f_permutation=2, f_coupling=1, leak=self.leak, device=device, gemm_impl=self.gemm_impl)
+                        f_permutation=2, f_coupling=1, leak=self.leak, device=device, gemm_impl=self.gemm_impl,
+                        train=train)
 
     def generate(self, z):
         """z [B,nz,1,1] or [B,nz] -> x_hat [B,nc,H,W] through the CUDA kernels (never records autograd)."""

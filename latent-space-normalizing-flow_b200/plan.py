@@ -37,15 +37,16 @@ def _check_tensor(t: torch.Tensor, name: str, device, shape=None):
 class Plan:
     def __init__(self, *, arch: str, batch: int, nz: int, ngf: int, nc: int, f_depth: int, f_width: int,
                  f_permutation: int, f_coupling: int, leak: float, device, gemm_impl: int = _cabi.GEMM_TCGEN05,
-                 bwd_passes: int = 0):
+                 bwd_passes: int = 0, train: bool = False):
         self.lib = _cabi.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("lsnf_b200 plans live on a CUDA device; there is no CPU fallback")
         self.cfg = _cabi.Config(arch=_cabi.ARCH[arch], batch=batch, nz=nz, ngf=ngf, nc=nc, f_depth=f_depth,
                                 f_width=f_width, f_permutation=f_permutation, f_coupling=f_coupling, leak=leak,
-                                gemm_impl=gemm_impl, bwd_passes=bwd_passes)
+                                gemm_impl=gemm_impl, bwd_passes=bwd_passes, train=int(bool(train)))
         self.arch, self.batch, self.nz, self.nc = arch, batch, nz, nc
+        self.train = bool(train)
         self.f_depth, self.f_permutation = f_depth, f_permutation
         handle = C.c_void_p()
         _cabi.check(self.lib.lsnf_plan_create(C.byref(self.cfg), C.byref(handle)), "lsnf_plan_create")
@@ -208,6 +209,33 @@ class Plan:
                                                    _stream(self.device)), "lsnf_sample_prior")
         return (x, z) if want_z else x
 
+    # ---- generator parameter update (train.py:390-398) -----------------------------------------------
+    def generator_grad_layout(self):
+        """[(offset, size)] inside the flat gradient buffer: layer l's weight gradient (the parameter's own
+        [C_in, C_out, k, k] layout) at index 2l, its bias gradient at 2l+1 (lsnf_generator_grad_layout)."""
+        n = 2 * len([s for s in self.stages() if s.kind == 0])
+        off, size = (C.c_int64 * n)(), (C.c_int64 * n)()
+        _cabi.check(self.lib.lsnf_generator_grad_layout(self.handle, off, size), "lsnf_generator_grad_layout")
+        return [(int(off[i]), int(size[i])) for i in range(n)]
+
+    def generator_param_grads(self, z: torch.Tensor, x: torch.Tensor, global_batch: int,
+                              flat: Optional[torch.Tensor] = None):
+        """Gradients of loss_g = mse_sum(G(z), x) / global_batch w.r.t. every generator weight and bias into one
+        flat fp32 buffer (returned with this rank's share of loss_g).  Needs ``train=True`` at plan creation and
+        ``ensure_generator`` on the current parameters."""
+        _check_tensor(z, "z", self.device, (self.batch, self.nz))
+        _check_tensor(x, "x", self.device, (self.batch, self.nc, self.img, self.img))
+        n = int(self.lib.lsnf_generator_grad_floats(self.handle))
+        if flat is None:
+            flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        _check_tensor(flat, "flat gradient buffer", self.device, (n,))
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.lsnf_generator_param_grads(self.handle, z.data_ptr(), x.data_ptr(), int(global_batch),
+                                                            flat.data_ptr(), loss.data_ptr(), _stream(self.device)),
+                        "lsnf_generator_param_grads")
+        return flat, loss
+
     # ---- flow parameter update (train.py:403-415) ----------------------------------------------------
     def flow_grad_layout(self):
         """[(offset, size)] of every flow parameter gradient inside the flat buffer, step-major, in the order of
@@ -282,21 +310,21 @@ def default_bwd_passes(noisy_chain: bool = False) -> int:
 
 
 def get_plan(*, arch, batch, nz, ngf, nc, f_depth, f_width, f_permutation, f_coupling, leak, device,
-             gemm_impl=_cabi.GEMM_TCGEN05, bwd_passes=None) -> Plan:
+             gemm_impl=_cabi.GEMM_TCGEN05, bwd_passes=None, train=False) -> Plan:
     device = torch.device(device)
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
     if bwd_passes is None:
         bwd_passes = default_bwd_passes()
     key = (str(device), arch, batch, nz, ngf, nc, f_depth, f_width, f_permutation, f_coupling, float(leak), gemm_impl,
-           bwd_passes)
+           bwd_passes, bool(train))
     p = _PLANS.get(key)
     if p is None:
         if len(_PLANS) > 16:
             _PLANS.pop(next(iter(_PLANS)))
         p = Plan(arch=arch, batch=batch, nz=nz, ngf=ngf, nc=nc, f_depth=f_depth, f_width=f_width,
                  f_permutation=f_permutation, f_coupling=f_coupling, leak=leak, device=device, gemm_impl=gemm_impl,
-                 bwd_passes=bwd_passes)
+                 bwd_passes=bwd_passes, train=train)
         _PLANS[key] = p
     return p
 

@@ -1,10 +1,9 @@
-"""One training iteration of the reference (train.py:376-415) with the Langevin posterior inference on the CUDA
-path and data parallelism over the latent batch.
-
-Only the Langevin call is in the hot-path scope; the generator and flow parameter updates stay
-in torch autograd exactly as upstream (section 8f lists their kernels as next).  What this module adds is the
-glue a multi-GPU run needs: each rank infers the latents of its shard (no collective), computes its local losses,
-and the parameter gradients are summed across ranks with one flat all-reduce per network (NCCL over NVLink).
+"""One training iteration of the reference (train.py:376-415) on the CUDA path, with data parallelism over the
+latent batch: Langevin posterior inference (``lsnf_langevin_run``), the flow parameter update (``flow_update``:
+``lsnf_flow_param_grads`` + fused Adam) and the generator parameter update.  Each rank
+infers the latents of its shard (no collective) and computes its share of the parameter gradients into ONE flat
+buffer per network, which is summed across ranks with a single all-reduce (NCCL over NVLink) before the fused Adam
+step.
 """
 from __future__ import annotations
 
@@ -16,16 +15,111 @@ import torch.distributed as dist
 
 from .dist import allreduce_grads
 from .langevin import sample_langevin_post_z_with_flow
+from .optim import FusedAdam
+from .plan import _FLOW_PARAM_ORDER
 
 
 def make_optimizers(netG, netF, args):
-    """train.py:294-295."""
+    """train.py:294-295: Adam for both networks.  ``FusedAdam`` is a ``torch.optim.Adam`` (same state_dict, same
+    ``step()``) that the fused update kernels can drive directly."""
     g = lambda k, d: args.get(k, d) if isinstance(args, dict) else getattr(args, k, d)
-    optG = torch.optim.Adam(netG.parameters(), lr=g("g_lr", 0.0004), weight_decay=g("g_decay", 0),
-                            betas=(g("g_beta1", 0.5), g("g_beta2", 0.999)))
-    optF = torch.optim.Adam(netF.parameters(), lr=g("f_lr", 0.0004), weight_decay=g("f_decay", 0),
-                            betas=(g("f_beta1", 0.5), g("f_beta2", 0.999)))
+    optG = FusedAdam(netG.parameters(), lr=g("g_lr", 0.0004), weight_decay=g("g_decay", 0),
+                     betas=(g("g_beta1", 0.5), g("g_beta2", 0.999)))
+    optF = FusedAdam(netF.parameters(), lr=g("f_lr", 0.0004), weight_decay=g("f_decay", 0),
+                     betas=(g("f_beta1", 0.5), g("f_beta2", 0.999)))
     return optG, optF
+
+
+def generator_gradients(netG, z_k, x, global_batch, plan=None):
+    """(flat gradient buffer, [(parameter, gradient view)], this rank's share of loss_g) of
+    loss_g = mse_sum(G(z_k), x) / global_batch (train.py:392-394) through ``lsnf_generator_param_grads``: forward,
+    data-gradient chain and one weight-gradient tap-GEMM per layer on the tensor cores."""
+    b = z_k.shape[0]
+    z2 = z_k.detach().reshape(b, netG.nz).contiguous().float()
+    xx = x.detach().contiguous().float()
+    if plan is None:
+        plan = netG._plan(b, z2.device, train=True)
+    plan.ensure_generator(netG)
+    flat = getattr(plan, "_ggrad_flat", None)
+    if flat is None:
+        flat = plan._ggrad_flat = torch.zeros(int(plan.lib.lsnf_generator_grad_floats(plan.handle)),
+                                              dtype=torch.float32, device=z2.device)
+    flat, loss = plan.generator_param_grads(z2, xx, global_batch, flat)
+    convs = [m for m in netG.gen if isinstance(m, torch.nn.ConvTranspose2d)]
+    params = [p for m in convs for p in (m.weight, m.bias)]
+    pairs = [(p, flat[off:off + size].view_as(p)) for (off, size), p in zip(plan.generator_grad_layout(), params)]
+    return flat, pairs, loss
+
+
+def generator_update(netG, optG, z_k, x, args, *, global_batch=None, group=None, world=1, plan=None):
+    """The generator step of train.py:390-398 without autograd.  Returns loss_g."""
+    g = lambda k, d: args.get(k, d) if isinstance(args, dict) else getattr(args, k, d)
+    b_global = z_k.shape[0] if global_batch is None else int(global_batch)
+    flat, pairs, loss = generator_gradients(netG, z_k, x, b_global, plan=plan)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    scale = None
+    if g("g_is_grad_clamp", False):   # train.py:396-397 (upstream names an undefined `opt` there; intended semantics)
+        scale = torch.clamp(float(g("g_max_norm", 100)) / (torch.linalg.vector_norm(flat) + 1e-6), max=1.0)
+    params, grads = [p for p, _ in pairs], [v for _, v in pairs]
+    if isinstance(optG, FusedAdam):
+        optG.fused_step(params, grads, grad_scale=scale)
+    else:
+        for p, v in pairs:
+            p.grad = v.clone() if scale is None else v * scale
+        optG.step()
+    return loss
+
+
+def flow_params_in_order(netF):
+    """The flow parameters in the order of the flat gradient buffer (``Plan.flow_grad_layout``): per step, the twelve
+    tensors of ``_FLOW_PARAM_ORDER``; ``None`` where a step has no such parameter (shuffle permutation)."""
+    out = []
+    for st in netF.revnet2d_s[0].revnet2d_step_s:
+        sd = dict(st.named_parameters())
+        for k in _FLOW_PARAM_ORDER:
+            out.append(sd.get(k) if not (k == "invertible_1x1_conv.w" and netF.f_permutation != 2) else None)
+    return out
+
+
+def flow_gradients(netF, z_k, global_batch):
+    """(flat gradient buffer, [(parameter, gradient view)], this rank's share of loss_f) of
+    loss_f = -(1/global_batch) sum_b log p(z_b) (train.py:403-410) through ``lsnf_flow_param_grads``."""
+    b = z_k.shape[0]
+    z2 = z_k.detach().reshape(b, netF.nz).contiguous().float()
+    plan = netF._plan(b, z2.device)
+    plan.ensure_flow(netF, need_inverse=True)
+    flat = getattr(plan, "_fgrad_flat", None)
+    if flat is None:
+        flat = plan._fgrad_flat = torch.zeros(int(plan.lib.lsnf_flow_grad_floats(plan.handle)), dtype=torch.float32,
+                                              device=z2.device)
+    flat, loss = plan.flow_param_grads(z2, global_batch, flat)
+    pairs = [(p, flat[off:off + size].view_as(p)) for (off, size), p in zip(plan.flow_grad_layout(),
+                                                                            flow_params_in_order(netF)) if p is not None]
+    return flat, pairs, loss
+
+
+def flow_update(netF, optF, z_k, args, *, global_batch=None, group=None, world=1):
+    """The flow step of train.py:403-415 without autograd: gradients by the fused flow kernel + batch reductions,
+    one all-reduce of the flat buffer across ranks, optional norm clipping, fused Adam.  Returns loss_f."""
+    g = lambda k, d: args.get(k, d) if isinstance(args, dict) else getattr(args, k, d)
+    b_global = z_k.shape[0] if global_batch is None else int(global_batch)
+    flat, pairs, loss = flow_gradients(netF, z_k, b_global)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    scale = None
+    if g("f_is_grad_clamp", False):   # train.py:411-412, clip_grad_norm_ semantics
+        scale = torch.clamp(float(g("f_max_norm", 100)) / (torch.linalg.vector_norm(flat) + 1e-6), max=1.0)
+    params, grads = [p for p, _ in pairs], [v for _, v in pairs]
+    if isinstance(optF, FusedAdam):
+        optF.fused_step(params, grads, grad_scale=scale)
+    else:   # any other torch optimizer: hand it the same gradients
+        for p, v in pairs:
+            p.grad = v.clone() if scale is None else v * scale
+        optF.step()
+    return loss
 
 
 _iter_counter = [0]
@@ -73,26 +167,12 @@ def training_iteration(x, netG, netF, optG, optF, args, *, global_batch=None, sa
         gen = torch.Generator(x.device).manual_seed(int(seed) & (2 ** 63 - 1))
         z0 = torch.randn(b_global, netG.nz, 1, 1, device=x.device, generator=gen)[sample_offset:sample_offset + b_local]
     z_k, gn, fn = sample_langevin_post_z_with_flow(z0, x, netG, netF, args, seed=seed,
-                                                   sample_offset=sample_offset)          # train.py:387
-    # generator update (train.py:390-398); autograd branch of _netG.forward
-    optG.zero_grad()
-    x_hat = netG(z_k.detach())
-    loss_g = torch.nn.functional.mse_loss(x_hat, x, reduction="sum") / b_global
-    loss_g.backward()
-    if world > 1:
-        allreduce_grads(netG.parameters(), group=group)
-    if g("g_is_grad_clamp", False):   # train.py:396-397 (upstream names an undefined `opt` there; intended semantics)
-        torch.nn.utils.clip_grad_norm_(netG.parameters(), g("g_max_norm", 100))
-    optG.step()
-    # flow update (train.py:403-415)
-    optF.zero_grad()
-    z1, logdet, _ = netF(torch.squeeze(z_k).reshape(b_local, -1), objective=torch.zeros(b_local, device=x.device))
-    ll = (-0.5 * z1 ** 2).flatten(1).sum(-1) + np.log(2 * np.pi) + logdet
-    loss_f = -ll.sum() / b_global
-    loss_f.backward()
-    if world > 1:
-        allreduce_grads(netF.parameters(), group=group)
-    if g("f_is_grad_clamp", False):   # train.py:411-412
-        torch.nn.utils.clip_grad_norm_(netF.parameters(), g("f_max_norm", 100))
-    optF.step()
+                                                   sample_offset=sample_offset, train=True)   # train.py:387
+    from .langevin import langevin_plan
+    from .plan import default_bwd_passes
+    plan = langevin_plan(netG, netF, b_local, x.device, default_bwd_passes(), train=True)  # the plan that call used
+    # generator update (train.py:390-398): weight-gradient tap-GEMMs + one flat all-reduce + fused Adam
+    loss_g = generator_update(netG, optG, z_k, x, args, global_batch=b_global, group=group, world=world, plan=plan)
+    # flow update (train.py:403-415): gradient kernels + one flat all-reduce + fused Adam
+    loss_f = flow_update(netF, optF, z_k, args, global_batch=b_global, group=group, world=world)
     return loss_g.detach(), loss_f.detach(), gn, fn, z_k
