@@ -119,9 +119,12 @@ struct TransArgs {
   int P, B, H, W, C;
   long long s_plane, s_b, s_h, s_w;   // source strides (elements)
   int src_fp16, src_single;           // halves are fp16 (else bf16); the lo half is absent
-  int Hp, Wp, halo;
+  int Hp, Wp, halo;                   // destination grid of one sample: Hp x Wp, `halo` zero rows above and below
   long long Kp;                       // columns of one half of a destination row
   int c_rows;                         // destination rows per plane (>= C)
+  int xvar;                           // != 0: every source plane p is written twice -- as is (destination plane 2p) and
+                                      // shifted by one column (2p+1): to the right for odd p (reading column x yields
+                                      // g(x-1)), to the left for even p (g(x+1)); columns shifted in are zero
 };
 
 struct FinalizeArgs {

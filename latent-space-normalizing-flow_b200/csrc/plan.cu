@@ -435,14 +435,16 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         tg.P = 1; tg.B = B; tg.H = tg.W = y.hin; tg.C = BLOCK_K; tg.s_w = 2 * BLOCK_K; tg.s_h = (long long)y.hin * tg.s_w;
         tg.s_b = (long long)y.hin * tg.s_h; tg.c_rows = BLOCK_K;
       } else {
-        // k4/s2/p1: per tap, dW[ci][co] = sum_pos act[pos][ci] * gpre[plane_tap][pos + (dy, dx)][co]
-        w.a_rows = y.ci; hp = wp = y.hin + 2; halo = 1;
+        // k4/s2/p1: per tap, dW[ci][co] = sum_pos act[pos][ci] * gpre[plane_tap][pos + (dy, dx)][co].  One zero halo
+        // row above and below every sample (dy becomes the K offset dy * Wp, a multiple of 8 elements = 16 bytes as
+        // TMA box origins must be); dx picks the as-is or the column-shifted copy of the phase plane (TransArgs::xvar)
+        w.a_rows = y.ci; hp = y.hin + 2; wp = (int)align_up(y.hin, 8); halo = 1;
         w.Kp = (long long)align_up((size_t)B * hp * wp, BLOCK_K);
-        w.planes = 4; w.g_rows = y.co; w.ntaps = 16; n_cols = y.co; block_n = pick_block_n(y.co);
+        w.planes = 8; w.g_rows = y.co; w.ntaps = 16; n_cols = y.co; block_n = pick_block_n(y.co);
         ta.P = 1; ta.B = B; ta.H = ta.W = y.hin; ta.C = y.ci; ta.s_w = 2 * y.ci; ta.s_h = (long long)y.hin * ta.s_w;
         ta.s_b = (long long)y.hin * ta.s_h; ta.src_fp16 = 1; ta.c_rows = y.ci;
         tg.P = 4; tg.B = B; tg.H = tg.W = y.hin; tg.C = y.co; tg.s_w = 2 * y.co; tg.s_h = (long long)y.hin * tg.s_w;
-        tg.s_b = (long long)y.hin * tg.s_h; tg.s_plane = (long long)B * tg.s_b; tg.c_rows = y.co;
+        tg.s_b = (long long)y.hin * tg.s_h; tg.s_plane = (long long)B * tg.s_b; tg.c_rows = y.co; tg.xvar = 1;
       }
       ta.Hp = tg.Hp = hp; ta.Wp = tg.Wp = wp; ta.halo = tg.halo = halo; ta.Kp = tg.Kp = w.Kp;
       tg.src_fp16 = single ? 1 : 0; tg.src_single = single ? 1 : 0;
@@ -481,8 +483,8 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         up2_bwd_taps(y.co, tp);   // plane and (dy, dx) of every tap; brow = plane * C_out in the transposed gradient
         for (int t = 0; t < 16; ++t) {
           d.ph[0].taps[t].dy = 0; d.ph[0].taps[t].dx = 0; d.ph[0].taps[t].plane = 0;
-          d.ph[0].taps[t].bsh = (int16_t)(tp[t].dy * wp + tp[t].dx);
-          d.ph[0].taps[t].brow = tp[t].plane * y.co;
+          d.ph[0].taps[t].bsh = (int16_t)(tp[t].dy * wp);
+          d.ph[0].taps[t].brow = (tp[t].plane * 2 + (tp[t].dx != 0 ? 1 : 0)) * y.co;
         }
       }
       // results: dW in the parameter's own layout, then db
@@ -507,7 +509,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
             const bool once_x = y.s == 1 ? kx == y.p : (kx == 1 || kx == 2);
             if (once_y && once_x) r.sel[r.nsel++] = (ky * y.k + kx) * y.co;
           }
-      } else { r.nsel = 4; for (int q = 0; q < 4; ++q) r.sel[q] = q * y.co; }
+      } else { r.nsel = 4; for (int q = 0; q < 4; ++q) r.sel[q] = 2 * q * y.co; }   // the as-is copy of every plane
       if (first && w.ksplit != 1) { /* K = batch only: never split */ }
     }
     p->gen_grad_floats = goff;
@@ -762,8 +764,18 @@ extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const
   cudaStream_t s = (cudaStream_t)stream;
   const lsnf_config& c = plan->cfg;
   const int L = plan->n_layers;
+  // LSNF_SYNC_DEBUG=1: synchronise after every step and name the one that failed
+  static const bool dbg = [] { const char* e = getenv("LSNF_SYNC_DEBUG"); return e && e[0] == '1'; }();
+  auto check = [&](const char* what, int l) -> int {
+    if (!dbg) return 0;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) return 0;
+    set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " after " + what + " of layer " + std::to_string(l));
+    return LSNF_ERR_CUDA;
+  };
   // x_hat = G(z_k) (train.py:392) and loss_g = mse_sum / B (train.py:393)
   if ((rc = gen_forward(plan, z, nullptr, s, true))) return rc;
+  if ((rc = check("generator forward", -1))) return rc;
   const long long npix = (long long)c.batch * c.nc * plan->img * plan->img;
   if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch, loss, s)))
     return rc;
@@ -772,20 +784,22 @@ extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const
   if ((rc = launch_last_fused(plan, x, 1.f, s))) return rc;
   for (int i = L; i < 2 * L - 1; ++i)
     if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+  if ((rc = check("data-gradient chain", -1))) return rc;
   const float scale = 2.f / (float)global_batch;
   for (int l = L - 1; l >= 0; --l) {
     WgradLayer& w = plan->wg[l];
     TransArgs ta = w.ta, tg = w.tg;
     ta.src = (const uint16_t*)(plan->ws + (l == 0 ? plan->off_zhl : plan->off_act[l - 1]));
     tg.src = (const uint16_t*)(plan->ws + (l == L - 1 ? plan->off_im2col : plan->off_gpre[l]));
-    if ((rc = launch_transpose_hl(ta, s)) || (rc = launch_transpose_hl(tg, s))) return rc;
-    if ((rc = launch_tapgemm_tc(w.st, s))) return rc;
+    if ((rc = launch_transpose_hl(ta, s)) || (rc = check("activation transpose", l))) return rc;
+    if ((rc = launch_transpose_hl(tg, s)) || (rc = check("gradient transpose", l))) return rc;
+    if ((rc = launch_tapgemm_tc(w.st, s)) || (rc = check("weight-gradient tap-GEMM", l))) return rc;
     FinalizeArgs f = w.fin;
     f.out = grads + w.grad_w_off; f.scale = scale;
-    if ((rc = launch_wgrad_finalize(f, s))) return rc;
+    if ((rc = launch_wgrad_finalize(f, s)) || (rc = check("finalize", l))) return rc;
     RowSumArgs r = w.rs;
     r.out = grads + w.grad_b_off; r.scale = scale;
-    if ((rc = launch_bias_rowsum(r, s))) return rc;
+    if ((rc = launch_bias_rowsum(r, s)) || (rc = check("bias row sums", l))) return rc;
   }
   return LSNF_OK;
 }

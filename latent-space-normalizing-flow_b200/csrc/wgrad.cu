@@ -5,10 +5,13 @@
 // gradient of a ConvTranspose2d is then, per kernel tap (ky, kx),
 //     dW[ci][co][ky][kx] = sum_{b, iy, ix} act[b][iy][ix][ci] * gpre[b][iy*s - p + ky][ix*s - p + kx][co]
 // i.e. a GEMM whose K axis is (batch x positions).  The tcgen05 tap-GEMM wants K-major operands, so both tensors are
-// first TRANSPOSED to [channel][position] with the positions of every sample laid out on a zero-haloed grid
-// (Hp = H + 2, Wp = W + 2): a tap shift (dy, dx) then is the constant offset dy*Wp + dx along the flattened K axis,
-// out-of-image taps read the zero halo, and one 2-D TMA box per K block feeds each operand (wgrad stages of
-// tapgemm_tc_kernel).  Values are re-split to bf16 hi|lo pairs (fp32 range, 16 significant bits; 3 MMA passes).
+// first TRANSPOSED to [channel][position] with the positions of every sample laid out on a grid with one zero halo
+// row above and below (Hp = H + 2, Wp = W rounded up to 8): a vertical tap shift dy then is the constant offset dy*Wp
+// along the flattened K axis and reads the zero halo outside the image.  TMA box origins must be 16-byte aligned
+// along the innermost axis (an odd element offset raises an illegal-instruction fault), so the horizontal shift
+// dx = +-1 cannot be a coordinate offset: the transposed gradient is stored twice per phase plane, as is and
+// pre-shifted by one column (`xvar`), and each tap picks its copy.  One 2-D TMA box per K block feeds each operand
+// (wgrad stages of tapgemm_tc_kernel).  Values are re-split to bf16 hi|lo pairs (fp32 range, 16 significant bits; 3 MMA passes).
 // A finalize kernel sums the split-K partials and writes the gradient in the parameter's own [C_in][C_out][k][k]
 // layout; bias gradients are row sums of the transposed gradient.
 #include <algorithm>
@@ -57,15 +60,22 @@ __global__ void __launch_bounds__(256) transpose_hl_kernel(TransArgs a) {
     const int cr = tid >> 2, pq = tid & 3;          // channel row, group of 8 positions
     const int c = c0 + cr;
     if (c < a.C) {
-      uint16_t* row = a.dst + ((long long)p * a.c_rows + c) * 2 * a.Kp;
+      const int nvar = a.xvar ? 2 : 1;
+      uint16_t* row = a.dst + ((long long)p * nvar * a.c_rows + c) * 2 * a.Kp;
+      uint16_t* row1 = row + (long long)a.c_rows * 2 * a.Kp;   // the column-shifted copy
+      const int sh = (p & 1) ? 1 : -1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const long long pos = pos0 + pq * 8 + j;
         if (pos < npos) {
           const int x = (int)(pos % a.W), y = (int)((pos / a.W) % a.H), b = (int)(pos / ((long long)a.W * a.H));
-          const long long k = ((long long)b * a.Hp + y + a.halo) * a.Wp + x + a.halo;
+          const long long k = ((long long)b * a.Hp + y + a.halo) * a.Wp + x;
           row[k] = hi[cr][pq * 8 + j];
           row[a.Kp + k] = lo[cr][pq * 8 + j];
+          if (a.xvar && x + sh >= 0 && x + sh < a.W) {
+            row1[k + sh] = hi[cr][pq * 8 + j];
+            row1[a.Kp + k + sh] = lo[cr][pq * 8 + j];
+          }
         }
       }
     }

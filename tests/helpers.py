@@ -70,7 +70,8 @@ def build_nets(c, device="cuda:0", impl=0, seed=1):
     from lsnf_b200 import synth
     args = lsnf_b200.make_args(dataset=c["dataset"], nz=c["nz"], ngf=c["ngf"], f_width=c.get("f_width", 64),
                                f_flow_coupling=c.get("coupling", 1), f_flow_permutation=c.get("permutation", 2),
-                               g_llhd_sigma=c.get("sigma", 0.3), g_l_steps=c.get("T", 20))
+                               g_llhd_sigma=c.get("sigma", 0.3), g_l_steps=c.get("T", 20),
+                               g_activation_leak=c.get("leak", 0.2))
     netG = lsnf_b200._netG(args).to(device).eval()
     netF = lsnf_b200._netF(args, nz=c["nz"]).to(device).eval()
     netG.load_state_dict(to_torch(synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=seed)))

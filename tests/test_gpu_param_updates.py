@@ -148,6 +148,7 @@ def assert_params_close(got, want, lr, steps, what):
     assert float(d.max()) <= 2.2 * lr * steps, (what, float(d.max()))
 
 
+@pytest.mark.parametrize("leak", [1.0, 0.2])
 @pytest.mark.parametrize("c,B", [
     (dict(dataset="svhn", nz=100, ngf=64), 100),            # BASELINE config 1
     (dict(dataset="cifar10", nz=128, ngf=128), 100),        # BASELINE config 2 (headline)
@@ -155,7 +156,15 @@ def assert_params_close(got, want, lr, steps, what):
     (dict(dataset="svhn", nz=100, ngf=32), 37),             # C_in = 64 < one M tile in the last layer
     (dict(dataset="celeba_hq256", nz=100, ngf=64), 2),      # seven layers, 128-wide last grid
 ])
-def test_generator_parameter_gradients_match_autograd(c, B):
+def test_generator_parameter_gradients_match_autograd(c, B, leak):
+    # leak = 1.0 makes the generator kink-free (LeakyReLU(1.0) is the identity): every weight and bias gradient must
+    # then agree with autograd to 1e-4 relative -- that is the arithmetic of the transposes, the weight-gradient
+    # tap-GEMMs, the split-K finalize and the bias row sums.  With the reference's leak = 0.2 the gradient of a hidden
+    # unit whose pre-activation is zero to within rounding error jumps by 1/leak (helpers.assert_grad_close); one such
+    # unit moves a small-batch weight gradient by ~1e-3 relative, and the reference's own fp32 and fp64 gradients
+    # differ by up to 7e-4 at the CIFAR-10 shape.  There the last layer (nothing kinked
+    # downstream of it) is held to 1e-4 and the hidden layers to a kink's worth.
+    c = dict(c, leak=leak)
     args, netG, netF = build_nets(c, DEV, seed=4)
     img = synth.image_size(c["dataset"])
     x_np, z_np, _ = synth.inputs(B, c["nz"], 3, img, 1, seed=9)
@@ -164,21 +173,18 @@ def test_generator_parameter_gradients_match_autograd(c, B):
     gp = to_torch(synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=4))
     leaves = {k: v.clone().requires_grad_(True) for k, v in gp.items()}
     layers = refpath.generator_layers(c["dataset"], c["nz"], c["ngf"])
-    x_hat = refpath.generator_forward(leaves, z, layers)                               # train.py:392
+    x_hat = refpath.generator_forward(leaves, z, layers, leak)                         # train.py:392
     want = torch.nn.functional.mse_loss(x_hat, x, reduction="sum") / B                 # train.py:393
     want.backward()
     assert abs(loss.item() - want.item()) < REL_TOL * want.item()
     named = dict(netG.named_parameters())
     got = {id(p): g for p, g in pairs}
-    worst = {}
-    for k in leaves:
-        e = rel_l2(got[id(named[k])].cpu(), leaves[k].grad)
-        worst[k] = e
-    print(f"generator parameter gradients {c['dataset']} ngf={c['ngf']} B={B}: " +
-          ", ".join(f"{k} {e:.1e}" for k, e in worst.items()))
-    # LeakyReLU sign flips of near-zero pre-activations (helpers.assert_grad_close) touch single rows of a weight
-    # gradient; per tensor that is far below the tolerance
-    assert max(worst.values()) < REL_TOL, worst
+    errs = {k: rel_l2(got[id(named[k])].cpu(), leaves[k].grad) for k in leaves}
+    print(f"generator parameter gradients {c['dataset']} ngf={c['ngf']} B={B} leak={leak}: " +
+          ", ".join(f"{k} {e:.1e}" for k, e in errs.items()))
+    last = f"gen.{3 * (len(layers) - 1)}."
+    for k, e in errs.items():
+        assert e < (REL_TOL if (leak == 1.0 or k.startswith(last)) else 1e-2), (k, e)
 
 
 def test_generator_update_matches_torch_adam_over_several_iterations():
