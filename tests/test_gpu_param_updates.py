@@ -187,13 +187,29 @@ def test_generator_parameter_gradients_match_autograd(c, B, leak):
         assert e < (REL_TOL if (leak == 1.0 or k.startswith(last)) else 1e-2), (k, e)
 
 
-def test_generator_update_matches_torch_adam_over_several_iterations():
-    c = dict(dataset="svhn", nz=100, ngf=64)
+def assert_updates_agree(got, want, start, lr, steps, what, strict):
+    """strict (kink-free generator): element-wise agreement as assert_params_close.  With LeakyReLU kinks the gradient
+    itself is only defined up to the sign decisions of near-zero pre-activations (see the gradient test above), and
+    Adam turns every element's gradient into a step of size ~lr whatever its magnitude, so element-wise agreement is
+    not a meaningful demand; the two updates must then point the same way (cosine > 0.8) and respect the step bound."""
+    if strict:
+        return assert_params_close(got, want, lr, steps, what)
+    du, dr = (got - start).flatten().double(), (want - start).flatten().double()
+    cos = float((du @ dr) / (du.norm() * dr.norm() + 1e-30))
+    d = (got - want).abs()
+    print(f"{what}: update cosine {cos:.4f}, max |diff| {float(d.max()):.2e}, fraction above 2e-5: {float((d > 2e-5).float().mean()):.2e}")
+    assert cos > 0.8 and float(d.max()) <= 2.2 * lr * steps, (what, cos)
+
+
+@pytest.mark.parametrize("leak", [1.0, 0.2])
+def test_generator_update_matches_torch_adam_over_several_iterations(leak):
+    c = dict(dataset="svhn", nz=100, ngf=64, leak=leak)
     B, lr = 100, 0.0004
     args, netG, netF = build_nets(c, DEV, seed=6)
     netG.train()
     optG, _ = lsnf_b200.make_optimizers(netG, netF, args)
     gp = to_torch(synth.generator_state("svhn", 100, 64, 3, seed=6))
+    start = {k: v.clone() for k, v in gp.items()}
     leaves = {k: v.clone().requires_grad_(True) for k, v in gp.items()}
     ref_opt = torch.optim.Adam(list(leaves.values()), lr=lr, betas=(0.5, 0.999))      # train.py:294
     layers = refpath.generator_layers("svhn", 100, 64)
@@ -202,25 +218,26 @@ def test_generator_update_matches_torch_adam_over_several_iterations():
         z, x = torch.from_numpy(z_np), torch.from_numpy(x_np)
         loss = lsnf_b200.generator_update(netG, optG, z.to(DEV), x.to(DEV), args)
         ref_opt.zero_grad()
-        want = torch.nn.functional.mse_loss(refpath.generator_forward(leaves, z, layers), x, reduction="sum") / B
+        want = torch.nn.functional.mse_loss(refpath.generator_forward(leaves, z, layers, leak), x, reduction="sum") / B
         want.backward()
         ref_opt.step()
         assert abs(loss.item() - want.item()) < 1e-3 * want.item()
     named = dict(netG.named_parameters())
     for k in leaves:
-        assert_params_close(named[k].detach().cpu(), leaves[k].detach(), lr, 3, k)
+        assert_updates_agree(named[k].detach().cpu(), leaves[k].detach(), start[k], lr, 3, k, strict=(leak == 1.0))
     # the kernels see the updated weights (re-packed on the version bump)
     netG.eval()
     z = torch.randn(5, 100, 1, 1, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         xh = netG(z.to(DEV))
-    want = refpath.generator_forward({k: v.detach() for k, v in leaves.items()}, z, layers)
-    assert float((xh.cpu() - want).abs().max()) < 2e-3      # a few weights differ by a full Adam step (see above)
+    want = refpath.generator_forward({k: v.detach().cpu() for k, v in named.items()}, z, layers, leak)
+    assert float((xh.cpu() - want).abs().max()) < 1e-4
 
 
-def test_training_iteration_matches_the_reference_iteration_on_the_oracle():
+@pytest.mark.parametrize("leak", [1.0, 0.2])
+def test_training_iteration_matches_the_reference_iteration_on_the_oracle(leak):
     # one whole iteration of train.py:376-415 -- Langevin, G step, F step -- kernels vs oracle + autograd + torch Adam
-    c = dict(dataset="svhn", nz=100, ngf=64, T=20, sigma=0.3)
+    c = dict(dataset="svhn", nz=100, ngf=64, T=20, sigma=0.3, leak=leak)
     B, lr = 100, 0.0004
     args, netG, netF = build_nets(c, DEV, seed=2)
     optG, optF = lsnf_b200.make_optimizers(netG, netF, args)
@@ -230,7 +247,8 @@ def test_training_iteration_matches_the_reference_iteration_on_the_oracle():
     eps = np.stack([philox.langevin_noise(seed, 0, B, 100, t) for t in range(20)]).reshape(20, B, 100, 1, 1).astype(np.float32)
     lg, lf, gn, fn, zk = lsnf_b200.training_iteration(torch.from_numpy(x_np).to(DEV), netG, netF, optG, optF, args,
                                                       seed=seed, z0=torch.from_numpy(z0_np).to(DEV))
-    gp = {k: v.clone().requires_grad_(True) for k, v in to_torch(synth.generator_state("svhn", 100, 64, 3, seed=2)).items()}
+    g0 = to_torch(synth.generator_state("svhn", 100, 64, 3, seed=2))
+    gp = {k: v.clone().requires_grad_(True) for k, v in g0.items()}
     fsd = synth.flow_state(100, 64, 5, 1, 2, seed=2)
     fkeys = _param_keys(fsd)
     fp = {k: torch.from_numpy(np.ascontiguousarray(v)).clone() for k, v in fsd.items()}
@@ -238,18 +256,18 @@ def test_training_iteration_matches_the_reference_iteration_on_the_oracle():
     layers = refpath.generator_layers("svhn", 100, 64)
     z_ref, _, _ = refpath.langevin(torch.from_numpy(z0_np), torch.from_numpy(x_np), {k: v.detach() for k, v in gp.items()},
                                    {k: v.detach() for k, v in fp.items()}, layers, depth=5, steps=20, step_size=0.1,
-                                   sigma=0.3, eps=torch.from_numpy(eps))
+                                   sigma=0.3, eps=torch.from_numpy(eps), leak=leak)
     assert rel_l2(zk.cpu(), z_ref) < REL_TOL
     og = torch.optim.Adam(list(gp.values()), lr=lr, betas=(0.5, 0.999))
     of = torch.optim.Adam(fleaves, lr=lr, betas=(0.5, 0.999))
     x = torch.from_numpy(x_np)
-    loss_g = torch.nn.functional.mse_loss(refpath.generator_forward(gp, z_ref, layers), x, reduction="sum") / B
+    loss_g = torch.nn.functional.mse_loss(refpath.generator_forward(gp, z_ref, layers, leak), x, reduction="sum") / B
     loss_g.backward(); og.step()
     loss_f = _oracle_flow_loss(fp, z_ref.reshape(B, 100), 1, 2, B)
     loss_f.backward(); of.step()
     assert abs(lg.item() - loss_g.item()) < 1e-3 * loss_g.item() and abs(lf.item() - loss_f.item()) < 1e-3 * abs(loss_f.item())
     ng, nf = dict(netG.named_parameters()), dict(netF.named_parameters())
     for k in gp:
-        assert_params_close(ng[k].detach().cpu(), gp[k].detach(), lr, 1, k)
+        assert_updates_agree(ng[k].detach().cpu(), gp[k].detach(), g0[k], lr, 1, k, strict=(leak == 1.0))
     for k in fkeys:
         assert_params_close(nf[k].detach().cpu(), fp[k].detach(), lr, 1, k)
