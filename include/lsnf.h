@@ -161,11 +161,14 @@ int lsnf_sample_prior(lsnf_plan* plan, const float* eps, float* x, float* z, int
  * occupies [offsets[2l], +sizes[2l]) in the parameter's own [C_in,C_out,k,k] layout and its bias gradient
  * [offsets[2l+1], +sizes[2l+1]) (lsnf_generator_grad_layout).  With several ranks each passes its shard and the GLOBAL
  * batch size; the buffers are then summed (one all-reduce).  loss (nullable, device float): this rank's share of
- * loss_g.  Runs the forward pass, the data-gradient chain and one weight-gradient tap-GEMM per layer; deterministic. */
+ * loss_g.  Runs the forward pass, the data-gradient chain and one weight-gradient tap-GEMM per layer; deterministic.
+ * part: -1 = everything; -2 = only the forward pass, the loss and the data-gradient chain; l >= 0 = only layer l's
+ * weight and bias gradient (after a -2 call on the same inputs) -- so that a data-parallel caller can start the
+ * all-reduce of a layer's gradients while the next layer's are being computed. */
 size_t lsnf_generator_grad_floats(const lsnf_plan* plan);
 int lsnf_generator_grad_layout(const lsnf_plan* plan, int64_t* offsets, int64_t* sizes);
 int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const float* x, int32_t global_batch, float* grads,
-                               float* loss, lsnf_stream stream);
+                               float* loss, int32_t part, lsnf_stream stream);
 /* Flow parameter gradients of loss_f = -(1 / global_batch) * sum_b ll_b(z_b) over this plan's batch z [B,nz]
  * (train.py:403-411; ll_b = log p(z_b) of lsnf_flow_forward).  grads: device buffer of lsnf_flow_grad_floats()
  * floats, ZERO-INITIALISED by the caller once (alignment padding is never written); tensor (step, i) -- i in the order

@@ -11,8 +11,8 @@ from .langevin import (AttrDict, langevin_plan, make_args, make_sampler, sample_
 from .model import _netF, _netG, weights_init_xavier  # noqa: F401
 from .plan import Plan, clear_plans, get_plan, invalidate_plans  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .train import (flow_gradients, flow_update, generator_gradients, generator_update, make_optimizers,  # noqa: F401
-                    training_iteration)
+from .train import (flow_gradients, flow_update, generator_gradients, generator_update, generator_update_begin,  # noqa: F401
+                    make_optimizers, training_iteration)
 
 __all__ = ["_netG", "_netF", "weights_init_xavier", "sample_langevin_post_z_with_flow", "make_sampler", "make_args",
            "sample_x", "training_iteration", "make_optimizers", "flow_update", "flow_gradients", "generator_update", "generator_gradients", "FusedAdam", "Plan", "get_plan", "clear_plans", "invalidate_plans", "langevin_plan", "AttrDict", "synth",

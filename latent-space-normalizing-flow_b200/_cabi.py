@@ -76,7 +76,7 @@ EXPORTS = {
     "lsnf_generator_grad_floats": (C.c_size_t, [C.c_void_p]),
     "lsnf_generator_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lsnf_generator_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                             C.c_void_p]),
+                                             C.c_int32, C.c_void_p]),
     "lsnf_flow_grad_floats": (C.c_size_t, [C.c_void_p]),
     "lsnf_flow_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lsnf_flow_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -755,15 +755,17 @@ extern "C" int lsnf_generator_grad_layout(const lsnf_plan* plan, int64_t* offset
 }
 
 extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const float* x, int32_t global_batch,
-                                          float* grads, float* loss, lsnf_stream stream) {
+                                          float* grads, float* loss, int32_t part, lsnf_stream stream) {
   int rc = need(plan, true, false);
   if (rc) return rc;
   if (plan->wg.empty()) return fail(LSNF_ERR_STATE, "plan was created without lsnf_config.train");
   if (plan->cfg.gemm_impl != LSNF_GEMM_TCGEN05) return fail(LSNF_ERR_UNSUPPORTED, "weight gradients need the tcgen05 path");
   if (!z || !x || !grads || global_batch <= 0) return fail(LSNF_ERR_INVALID, "bad argument");
+  if (part < -2 || part >= plan->n_layers) return fail(LSNF_ERR_INVALID, "part must be -1 (all), -2 (prologue) or a layer");
   cudaStream_t s = (cudaStream_t)stream;
   const lsnf_config& c = plan->cfg;
   const int L = plan->n_layers;
+  const bool prologue = part < 0, layers_all = part == -1;
   // LSNF_SYNC_DEBUG=1: synchronise after every step and name the one that failed
   static const bool dbg = [] { const char* e = getenv("LSNF_SYNC_DEBUG"); return e && e[0] == '1'; }();
   auto check = [&](const char* what, int l) -> int {
@@ -773,20 +775,24 @@ extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const
     set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " after " + what + " of layer " + std::to_string(l));
     return LSNF_ERR_CUDA;
   };
-  // x_hat = G(z_k) (train.py:392) and loss_g = mse_sum / B (train.py:393)
-  if ((rc = gen_forward(plan, z, nullptr, s, true))) return rc;
-  if ((rc = check("generator forward", -1))) return rc;
-  const long long npix = (long long)c.batch * c.nc * plan->img * plan->img;
-  if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch, loss, s)))
-    return rc;
-  // backward through the generator: seed (x_hat - x)(1 - x_hat^2) unscaled; the factor 2 / B of the loss is applied
-  // in fp32 when the gradients are finalized.  The first layer's data gradient is not needed.
-  if ((rc = launch_last_fused(plan, x, 1.f, s))) return rc;
-  for (int i = L; i < 2 * L - 1; ++i)
-    if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
-  if ((rc = check("data-gradient chain", -1))) return rc;
+  if (prologue) {
+    // x_hat = G(z_k) (train.py:392) and loss_g = mse_sum / B (train.py:393)
+    if ((rc = gen_forward(plan, z, nullptr, s, true))) return rc;
+    if ((rc = check("generator forward", -1))) return rc;
+    const long long npix = (long long)c.batch * c.nc * plan->img * plan->img;
+    if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch, loss, s)))
+      return rc;
+    // backward through the generator: seed (x_hat - x)(1 - x_hat^2) unscaled; the factor 2 / B of the loss is applied
+    // in fp32 when the gradients are finalized.  The first layer's data gradient is not needed.
+    if ((rc = launch_last_fused(plan, x, 1.f, s))) return rc;
+    for (int i = L; i < 2 * L - 1; ++i)
+      if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+    if ((rc = check("data-gradient chain", -1))) return rc;
+    if (!layers_all) return LSNF_OK;
+  }
   const float scale = 2.f / (float)global_batch;
   for (int l = L - 1; l >= 0; --l) {
+    if (!layers_all && l != part) continue;
     WgradLayer& w = plan->wg[l];
     TransArgs ta = w.ta, tg = w.tg;
     ta.src = (const uint16_t*)(plan->ws + (l == 0 ? plan->off_zhl : plan->off_act[l - 1]));

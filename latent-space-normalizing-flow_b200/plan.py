@@ -219,21 +219,23 @@ class Plan:
         return [(int(off[i]), int(size[i])) for i in range(n)]
 
     def generator_param_grads(self, z: torch.Tensor, x: torch.Tensor, global_batch: int,
-                              flat: Optional[torch.Tensor] = None):
+                              flat: Optional[torch.Tensor] = None, part: int = -1, loss: Optional[torch.Tensor] = None):
         """Gradients of loss_g = mse_sum(G(z), x) / global_batch w.r.t. every generator weight and bias into one
         flat fp32 buffer (returned with this rank's share of loss_g).  Needs ``train=True`` at plan creation and
-        ``ensure_generator`` on the current parameters."""
+        ``ensure_generator`` on the current parameters.  ``part``: -1 everything; -2 forward + loss + data-gradient
+        chain only; l >= 0 only layer l's gradients (include/lsnf.h)."""
         _check_tensor(z, "z", self.device, (self.batch, self.nz))
         _check_tensor(x, "x", self.device, (self.batch, self.nc, self.img, self.img))
         n = int(self.lib.lsnf_generator_grad_floats(self.handle))
         if flat is None:
             flat = torch.zeros(n, dtype=torch.float32, device=self.device)
         _check_tensor(flat, "flat gradient buffer", self.device, (n,))
-        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        if loss is None:
+            loss = torch.empty((), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.lsnf_generator_param_grads(self.handle, z.data_ptr(), x.data_ptr(), int(global_batch),
-                                                            flat.data_ptr(), loss.data_ptr(), _stream(self.device)),
-                        "lsnf_generator_param_grads")
+                                                            flat.data_ptr(), loss.data_ptr(), int(part),
+                                                            _stream(self.device)), "lsnf_generator_param_grads")
         return flat, loss
 
     # ---- flow parameter update (train.py:403-415) ----------------------------------------------------

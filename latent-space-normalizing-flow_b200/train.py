@@ -30,10 +30,19 @@ def make_optimizers(netG, netF, args):
     return optG, optF
 
 
-def generator_gradients(netG, z_k, x, global_batch, plan=None):
-    """(flat gradient buffer, [(parameter, gradient view)], this rank's share of loss_g) of
-    loss_g = mse_sum(G(z_k), x) / global_batch (train.py:392-394) through ``lsnf_generator_param_grads``: forward,
-    data-gradient chain and one weight-gradient tap-GEMM per layer on the tensor cores."""
+_comm_streams = {}
+
+
+def _comm_stream(device):
+    """One side stream per device on which the gradient all-reduces are issued, so that they overlap the kernels the
+    main stream keeps launching (the remaining layers' weight gradients, the flow update)."""
+    key = (device.type, device.index)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device)
+    return _comm_streams[key]
+
+
+def _gen_plan_and_buffers(netG, z_k, x, plan):
     b = z_k.shape[0]
     z2 = z_k.detach().reshape(b, netG.nz).contiguous().float()
     xx = x.detach().contiguous().float()
@@ -44,32 +53,81 @@ def generator_gradients(netG, z_k, x, global_batch, plan=None):
     if flat is None:
         flat = plan._ggrad_flat = torch.zeros(int(plan.lib.lsnf_generator_grad_floats(plan.handle)),
                                               dtype=torch.float32, device=z2.device)
-    flat, loss = plan.generator_param_grads(z2, xx, global_batch, flat)
     convs = [m for m in netG.gen if isinstance(m, torch.nn.ConvTranspose2d)]
     params = [p for m in convs for p in (m.weight, m.bias)]
-    pairs = [(p, flat[off:off + size].view_as(p)) for (off, size), p in zip(plan.generator_grad_layout(), params)]
+    layout = plan.generator_grad_layout()
+    pairs = [(p, flat[off:off + size].view_as(p)) for (off, size), p in zip(layout, params)]
+    return plan, z2, xx, flat, layout, pairs
+
+
+def generator_gradients(netG, z_k, x, global_batch, plan=None):
+    """(flat gradient buffer, [(parameter, gradient view)], this rank's share of loss_g) of
+    loss_g = mse_sum(G(z_k), x) / global_batch (train.py:392-394) through ``lsnf_generator_param_grads``: forward,
+    data-gradient chain and one weight-gradient tap-GEMM per layer on the tensor cores."""
+    plan, z2, xx, flat, layout, pairs = _gen_plan_and_buffers(netG, z_k, x, plan)
+    flat, loss = plan.generator_param_grads(z2, xx, global_batch, flat)
     return flat, pairs, loss
+
+
+class _PendingGeneratorUpdate:
+    """Gradients computed, all-reduces in flight on the comm stream; ``finish()`` waits for them and applies Adam."""
+
+    def __init__(self, netG, optG, args, flat, pairs, loss, handles):
+        self.netG, self.optG, self.args = netG, optG, args
+        self.flat, self.pairs, self.loss, self.handles = flat, pairs, loss, handles
+
+    def finish(self):
+        g = lambda k, d: self.args.get(k, d) if isinstance(self.args, dict) else getattr(self.args, k, d)
+        for h in self.handles:
+            h.wait()   # the CURRENT stream waits for the collective; the host does not block
+        scale = None
+        if g("g_is_grad_clamp", False):   # train.py:396-397 (upstream names an undefined `opt` there; intended semantics)
+            scale = torch.clamp(float(g("g_max_norm", 100)) / (torch.linalg.vector_norm(self.flat) + 1e-6), max=1.0)
+        params, grads = [p for p, _ in self.pairs], [v for _, v in self.pairs]
+        if isinstance(self.optG, FusedAdam):
+            self.optG.fused_step(params, grads, grad_scale=scale)
+        else:
+            for p, v in self.pairs:
+                p.grad = v.clone() if scale is None else v * scale
+            self.optG.step()
+        return self.loss
+
+
+def generator_update_begin(netG, optG, z_k, x, args, *, global_batch=None, group=None, world=1, plan=None):
+    """First half of the generator step of train.py:390-398: gradients, and with several ranks their all-reduce
+    started layer by layer (bucket = one layer's weight + bias gradient, last layer first) on a comm stream while the
+    main stream computes the next layer's weight gradient.  ``.finish()`` completes the step."""
+    b_global = z_k.shape[0] if global_batch is None else int(global_batch)
+    plan, z2, xx, flat, layout, pairs = _gen_plan_and_buffers(netG, z_k, x, plan)
+    if world <= 1:
+        flat, loss = plan.generator_param_grads(z2, xx, b_global, flat)
+        return _PendingGeneratorUpdate(netG, optG, args, flat, pairs, loss, [])
+    comm = _comm_stream(z2.device)
+    main = torch.cuda.current_stream(z2.device)
+    handles = []
+    flat, loss = plan.generator_param_grads(z2, xx, b_global, flat, part=-2)
+
+    def reduce_async(t):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev)
+            handles.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    reduce_async(loss)
+    n_layers = len(layout) // 2
+    for l in reversed(range(n_layers)):
+        plan.generator_param_grads(z2, xx, b_global, flat, part=l, loss=loss)
+        lo = layout[2 * l][0]
+        hi = layout[2 * l + 1][0] + layout[2 * l + 1][1]
+        reduce_async(flat[lo:hi])
+    return _PendingGeneratorUpdate(netG, optG, args, flat, pairs, loss, handles)
 
 
 def generator_update(netG, optG, z_k, x, args, *, global_batch=None, group=None, world=1, plan=None):
     """The generator step of train.py:390-398 without autograd.  Returns loss_g."""
-    g = lambda k, d: args.get(k, d) if isinstance(args, dict) else getattr(args, k, d)
-    b_global = z_k.shape[0] if global_batch is None else int(global_batch)
-    flat, pairs, loss = generator_gradients(netG, z_k, x, b_global, plan=plan)
-    if world > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-    scale = None
-    if g("g_is_grad_clamp", False):   # train.py:396-397 (upstream names an undefined `opt` there; intended semantics)
-        scale = torch.clamp(float(g("g_max_norm", 100)) / (torch.linalg.vector_norm(flat) + 1e-6), max=1.0)
-    params, grads = [p for p, _ in pairs], [v for _, v in pairs]
-    if isinstance(optG, FusedAdam):
-        optG.fused_step(params, grads, grad_scale=scale)
-    else:
-        for p, v in pairs:
-            p.grad = v.clone() if scale is None else v * scale
-        optG.step()
-    return loss
+    return generator_update_begin(netG, optG, z_k, x, args, global_batch=global_batch, group=group, world=world,
+                                  plan=plan).finish()
 
 
 def flow_params_in_order(netF):
@@ -171,8 +229,12 @@ def training_iteration(x, netG, netF, optG, optF, args, *, global_batch=None, sa
     from .langevin import langevin_plan
     from .plan import default_bwd_passes
     plan = langevin_plan(netG, netF, b_local, x.device, default_bwd_passes(), train=True)  # the plan that call used
-    # generator update (train.py:390-398): weight-gradient tap-GEMMs + one flat all-reduce + fused Adam
-    loss_g = generator_update(netG, optG, z_k, x, args, global_batch=b_global, group=group, world=world, plan=plan)
-    # flow update (train.py:403-415): gradient kernels + one flat all-reduce + fused Adam
+    # generator update (train.py:390-398): weight-gradient tap-GEMMs, per-layer all-reduces on the comm stream ...
+    pending = generator_update_begin(netG, optG, z_k, x, args, global_batch=b_global, group=group, world=world,
+                                     plan=plan)
+    # ... overlapped with the flow update (train.py:403-415): gradient kernels + one flat all-reduce + fused Adam.
+    # The two updates are independent (neither reads the other network's parameters), so finishing the generator's
+    # Adam step after the flow's changes nothing.
     loss_f = flow_update(netF, optF, z_k, args, global_batch=b_global, group=group, world=world)
+    loss_g = pending.finish()
     return loss_g.detach(), loss_f.detach(), gn, fn, z_k
