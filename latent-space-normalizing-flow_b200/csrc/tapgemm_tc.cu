@@ -23,6 +23,9 @@
 
 namespace lsnf {
 
+#ifndef LSNF_EXP_FWD2PASS
+#define LSNF_EXP_FWD2PASS 0   // 1: forward stages use weights' hi halves only; 2: activations' hi halves only
+#endif
 constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half the columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB per hi or lo half
@@ -423,6 +426,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t a_hi = da + 2 * k, a_lo = a_hi + (A_TILE_BYTES >> 4);
             const uint64_t b_hi = db + 2 * k, b_lo = b_hi + (Cfg::B_TILE_BYTES >> 4);
             if (three) {
+#if LSNF_EXP_FWD2PASS   // experiment builds only (tools/run_fwd2pass_ab.sh): drop one cross term of the forward stages
+              if (st.fp16) {
+                if (LSNF_EXP_FWD2PASS == 1) umma_bf16(tmem_base, a_lo, b_hi, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                else umma_bf16(tmem_base, a_hi, b_lo, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+                continue;
+              }
+#endif
               umma_bf16(tmem_base, a_lo, b_hi, idesc, (it > it0 || k > 0) ? 1u : 0u);
               umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
               umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
@@ -881,6 +892,14 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const uint64_t a_hi = da + 2 * k, a_lo = a_hi + (A_TILE_BYTES >> 4);
               const uint64_t b_hi = db + 2 * k, b_lo = b_hi + (P_B_TILE_BYTES >> 4);
               if (three) {
+#if LSNF_EXP_FWD2PASS
+                if (st.fp16) {
+                  if (LSNF_EXP_FWD2PASS == 1) umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+                  else umma2_bf16(d_tmem, a_hi, b_lo, idesc, (it > w.ka || k > 0) ? 1u : 0u);
+                  umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+                  continue;
+                }
+#endif
                 umma2_bf16(d_tmem, a_lo, b_hi, idesc, (it > w.ka || k > 0) ? 1u : 0u);
                 umma2_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
                 umma2_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
