@@ -22,18 +22,19 @@ LSNF_NO_GRAPH=1 timeout 600 python bench.py --steps 1 --warmup 3 --calls-per-ste
 LSNF_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 130 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 1 --warmup 3 --calls-per-step 1 --no-cpu-baseline --no-secondary --no-eager-ref > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launch rc=$?"; wc -l gpurun_out/launches_r2.csv
 timeout 300 python tools/prof_stage.py 1 2 5 6 > gpurun_out/plain_prof.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tapgemm_tc2_kernel -s 4 -c 4 -f -o gpurun_out/prof_r2_dominant python tools/prof_stage.py 1 2 5 6 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:tapgemm_tc2_kernel -s 4 -c 4 -f -o gpurun_out/prof_r2_dominant python tools/prof_stage.py 1 2 5 6 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -1 gpurun_out/ncu_full.log
-python tools/ncu_summarize.py gpurun_out/prof_r2_dominant.ncu-rep gpurun_out/r2_ncu_full_tapgemm_pair.json --dominant cifar10 100 1,2,5,6
+python tools/ncu_summarize.py gpurun_out/prof_r2_dominant.ncu-rep gpurun_out/r2_ncu_full_tapgemm_pair.json --dominant cifar10 100 1,2,5,6; rm -f gpurun_out/prof_r2_dominant.ncu-rep
 timeout 300 python tools/prof_stage.py 0 3 4 7 > gpurun_out/plain_prof_short.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tapgemm_tc_kernel -s 4 -c 4 -f -o gpurun_out/prof_r2_short python tools/prof_stage.py 0 3 4 7 > gpurun_out/ncu_short.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:tapgemm_tc_kernel -s 4 -c 4 -f -o gpurun_out/prof_r2_short python tools/prof_stage.py 0 3 4 7 > gpurun_out/ncu_short.log 2>&1
 echo "ncu short rc=$?"
-python tools/ncu_summarize.py gpurun_out/prof_r2_short.ncu-rep gpurun_out/r2_ncu_full_short_stages.json
+python tools/ncu_summarize.py gpurun_out/prof_r2_short.ncu-rep gpurun_out/r2_ncu_full_short_stages.json; rm -f gpurun_out/prof_r2_short.ncu-rep
 FLOW=1 timeout 300 python tools/prof_stage.py 0 > gpurun_out/plain_prof_flow.log 2>&1 &&
-FLOW=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:flow_forward_kernel|flow_inverse_kernel" -s 2 -c 2 -f -o gpurun_out/prof_r2_flow python tools/prof_stage.py 0 > gpurun_out/ncu_flow.log 2>&1
+FLOW=1 timeout 900 ncu --set full --clock-control none -k "regex:flow_forward_kernel|flow_inverse_kernel" -s 2 -c 2 -f -o gpurun_out/prof_r2_flow python tools/prof_stage.py 0 > gpurun_out/ncu_flow.log 2>&1
 echo "ncu flow rc=$?"
-python tools/ncu_summarize.py gpurun_out/prof_r2_flow.ncu-rep gpurun_out/r2_ncu_full_flow.json
+python tools/ncu_summarize.py gpurun_out/prof_r2_flow.ncu-rep gpurun_out/r2_ncu_full_flow.json; rm -f gpurun_out/prof_r2_flow.ncu-rep
 timeout 300 python tools/prof_train.py > gpurun_out/plain_prof_train.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:tapgemm_tc_kernel|transpose_hl|wgrad_finalize|bias_rowsum|flow_param_grad|adam_kernel|mse_sum" -s 30 -c 40 -f -o gpurun_out/prof_r2_train python tools/prof_train.py > gpurun_out/ncu_train.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k "regex:tapgemm_tc_kernel|transpose_hl|wgrad_finalize|bias_rowsum|flow_param_grad|adam_kernel|mse_sum" -s 30 -c 40 -f -o gpurun_out/prof_r2_train python tools/prof_train.py > gpurun_out/ncu_train.log 2>&1
 echo "ncu train rc=$?"
-python tools/ncu_summarize.py gpurun_out/prof_r2_train.ncu-rep gpurun_out/r2_ncu_full_param_updates.json
+python tools/ncu_summarize.py gpurun_out/prof_r2_train.ncu-rep gpurun_out/r2_ncu_full_param_updates.json; rm -f gpurun_out/prof_r2_train.ncu-rep
+du -sh gpurun_out
