@@ -47,13 +47,19 @@ def run_train_bench(a, w, ctx, sink):
     for i in range(max(a.warmup, 3)):
         out = step(i)
     ctx.barrier()
+    # R training iterations per timed step so that the K steps last >= 3 s (same R on every rank: the estimate is the
+    # max over ranks)
+    import math
+    est_ms = bench.timed_calls(ctx, lambda i: step(50 + i), 2) / 2
+    R = a.calls_per_step or max(1, min(64, math.ceil(bench.TARGET_TIMED_SECONDS * 1e3 / (a.steps * est_ms))))
+    n_iter = a.steps * R
     sampler.window_begin()
-    ms_total = bench.timed_calls(ctx, lambda i: step(100 + i), a.steps)
+    ms_total = bench.timed_calls(ctx, lambda i: step(100 + i), n_iter)
     sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
     lg, lf, gn, fn, zk = out
     assert torch.isfinite(zk).all() and torch.isfinite(lg) and torch.isfinite(lf)
-    value = world * B * T * a.steps / (ms_total * 1e-3)
+    value = world * B * T * n_iter / (ms_total * 1e-3)
 
     # the same iterations without the collectives (every rank updates from its own shard): what the all-reduces cost
     exposed_ms = None
@@ -62,8 +68,8 @@ def run_train_bench(a, w, ctx, sink):
         nodp = make_step(False)
         for i in range(3):
             nodp(i)
-        ms_nodp = bench.timed_calls(ctx, lambda i: nodp(200 + i), a.steps)
-        exposed_ms = (ms_total - ms_nodp) / a.steps
+        ms_nodp = bench.timed_calls(ctx, lambda i: nodp(200 + i), n_iter)
+        exposed_ms = (ms_total - ms_nodp) / n_iter
         # the generator's flat gradient buffer all-reduced alone
         n = sum(p.numel() for p in netG.parameters())
         buf = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -89,13 +95,13 @@ def run_train_bench(a, w, ctx, sink):
     e2e_step(0)
     ctx.barrier()
     t0 = time.perf_counter()
-    for i in range(a.steps):
+    for i in range(n_iter):
         e2e_step(1 + i)
     ctx.barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * a.steps / float(e2e_s.item())
+    e2e_value = world * B * T * n_iter / float(e2e_s.item())
     if rank != 0:
         return
 
@@ -111,15 +117,17 @@ def run_train_bench(a, w, ctx, sink):
     e1.record()
     torch.cuda.synchronize()
     langevin_ms = e0.elapsed_time(e1) / 5
-    iter_ms = ms_total / a.steps
+    iter_ms = ms_total / n_iter
+    n_layers = len([s for s in plan.stages() if s.kind == 0])
     line = {
         "metric": "train_iteration_latent_steps_per_sec", "value": value, "unit": "latent-steps/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": iter_ms, "higher_is_better": True,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "mode": "train",
         "dtype": "fp16-hi/lo-3pass-fwd+bf16-hi/lo-3pass-bwd-and-wgrad/f32-accumulate (fp32-equivalent); fp32 flow + Adam",
         "data": "synthetic", "config": bench.workload_config(a.workload, w),
         "details": {"what": "Langevin + generator update + flow update (train.py:376-415), parameter-gradient "
                             "all-reduces inside the timed region; B per GPU fixed, losses normalised by the global batch",
+                    "training_iterations_per_step": R, "ms_per_iteration": iter_ms,
                     "langevin_call_ms": langevin_ms, "updates_ms": iter_ms - langevin_ms,
                     "allreduce_exposed_ms_per_iteration": exposed_ms, "allreduce_alone": busbw,
                     "grad_bytes_per_iteration": {"generator": sum(p.numel() for p in netG.parameters()) * 4,
@@ -127,7 +135,12 @@ def run_train_bench(a, w, ctx, sink):
                     "loss_g": float(lg), "loss_f": float(lf), "timed_region_s": ms_total * 1e-3,
                     "l2": "flushed between iterations (256 MB written, inside the timed region)"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "latent-steps/s", "h2d_bytes_per_step": x_h.numel() * 4, "d2h_bytes_per_step": 8},
-        "gpu_launches": a.steps * (plan.launch_count(T) + 60),
+        "e2e": {"value": e2e_value, "unit": "latent-steps/s", "h2d_bytes_per_step": x_h.numel() * 4 * R,
+                "d2h_bytes_per_step": 8 * R},
+        # Langevin call + generator update (split_z, L forward stages, gather, loss, fused seed kernel, L-1 data-gradient
+        # stages, per layer 2 transposes + tap-GEMM + finalize + bias sums, 1 Adam launch) + flow update (fused kernel,
+        # parameter-gradient kernel, 2 Adam launches for its 60 tensors)
+        "gpu_launches": n_iter * (plan.launch_count(T) + (1 + n_layers + 1) + 1 + 1 + (n_layers - 1) + 5 * n_layers + 1
+                                  + 2 + 2),
     }
     sink.emit(line)

@@ -170,6 +170,7 @@ struct lsnf_plan {
   lsnf::FlowLayout fl;
   std::vector<lsnf::WgradLayer> wg;     // training plans only (cfg.train)
   size_t gen_grad_floats = 0;
+  bool wg_ready = false;                // the forward pass + data-gradient chain of lsnf_generator_param_grads ran
   lsnf::FlowStash fstash;
   lsnf::FlowGradLayout fgrad;
   size_t off_fstash = 0, off_fgrad = 0, off_floss = 0;
@@ -246,7 +247,8 @@ int launch_last_fused(const lsnf_plan* plan, const float* x, float seed_scale, c
 int launch_transpose_hl(const TransArgs& a, cudaStream_t s);
 int launch_wgrad_finalize(const FinalizeArgs& a, cudaStream_t s);
 int launch_bias_rowsum(const RowSumArgs& a, cudaStream_t s);
-int launch_mse_sum(const float* xh, const float* x, long long n, float scale, float* out, cudaStream_t s);
+int launch_mse_sum(const float* xh, const float* x, long long n, float scale, float* partial, unsigned int* ticket,
+                   float* out, cudaStream_t s);
 int launch_reduce_partial(const lsnf_plan* plan, float* grad_z, float scale, cudaStream_t s);
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                      const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,

@@ -665,6 +665,7 @@ extern "C" int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* 
     LSNF_CUDA(cudaMemcpyAsync(plan->ws + plan->off_bias[l], biases[l], (size_t)plan->layers[l].co * 4,
                               cudaMemcpyDeviceToDevice, s));
   plan->g_packed = true;
+  plan->wg_ready = false;   // activations and gradients in the workspace belong to the old weights
   return LSNF_OK;
 }
 
@@ -780,7 +781,10 @@ extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const
     if ((rc = gen_forward(plan, z, nullptr, s, true))) return rc;
     if ((rc = check("generator forward", -1))) return rc;
     const long long npix = (long long)c.batch * c.nc * plan->img * plan->img;
-    if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch, loss, s)))
+    // partial sums in the (idle) norm scratch of the update kernel, ticket next to its own
+    if (loss && (rc = launch_mse_sum((const float*)(plan->ws + plan->off_xhat), x, npix, 1.f / (float)global_batch,
+                                     (float*)(plan->ws + plan->off_flow_out),
+                                     (unsigned int*)(plan->ws + plan->off_scalars + 64), loss, s)))
       return rc;
     // backward through the generator: seed (x_hat - x)(1 - x_hat^2) unscaled; the factor 2 / B of the loss is applied
     // in fp32 when the gradients are finalized.  The first layer's data gradient is not needed.
@@ -788,8 +792,11 @@ extern "C" int lsnf_generator_param_grads(lsnf_plan* plan, const float* z, const
     for (int i = L; i < 2 * L - 1; ++i)
       if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
     if ((rc = check("data-gradient chain", -1))) return rc;
+    plan->wg_ready = true;
     if (!layers_all) return LSNF_OK;
   }
+  if (!plan->wg_ready)
+    return fail(LSNF_ERR_STATE, "a layer's gradients were requested before the forward / data-gradient part (part = -2)");
   const float scale = 2.f / (float)global_batch;
   for (int l = L - 1; l >= 0; --l) {
     if (!layers_all && l != part) continue;

@@ -1002,6 +1002,8 @@ static RingGeom ring_geometry(const StageDev& d) {
   const int total = d.ph[0].ntaps * (d.Ka / BLOCK_K);
   const int iters = d.ksplit > 1 ? d.it_per_split : total;
   // short loops: half an SM's shared memory at most, so two CTAs are resident; long loops: all of it
+  // (round-2 sweep at CIFAR-10: a third or all of the shared memory instead of half changes the short stages by
+  // -1 / +11 us; 128- or 64-wide tiles for the last layer's data gradient cost +10 / +43 us -- half it stays)
   const size_t budget = (iters <= 4 ? TC_SMEM_MAX / 2 : TC_SMEM_MAX) - TC_SMEM_EXTRA;
   int nst = (int)std::min<size_t>(budget / stage, (size_t)std::min(iters, TC_MAX_STAGES));
   nst = std::max(nst, 1);

@@ -7,13 +7,9 @@ step.
 """
 from __future__ import annotations
 
-import math
-
-import numpy as np
 import torch
 import torch.distributed as dist
 
-from .dist import allreduce_grads
 from .langevin import sample_langevin_post_z_with_flow
 from .optim import FusedAdam
 from .plan import _FLOW_PARAM_ORDER

@@ -271,3 +271,28 @@ def test_training_iteration_matches_the_reference_iteration_on_the_oracle(leak):
         assert_updates_agree(ng[k].detach().cpu(), gp[k].detach(), g0[k], lr, 1, k, strict=(leak == 1.0))
     for k in fkeys:
         assert_params_close(nf[k].detach().cpu(), fp[k].detach(), lr, 1, k)
+
+
+def test_generator_gradients_with_the_single_pass_data_gradient(monkeypatch):
+    # opt-in reduced-precision mode (LSNF_BWD_PASSES=1): the gradient tensors hold fp16 hi halves only; the transposes
+    # and weight-gradient GEMMs must read them as such.  Kink-free generator; tolerance = the 11-bit significand.
+    monkeypatch.setenv("LSNF_BWD_PASSES", "1")
+    lsnf_b200.clear_plans()
+    try:
+        c = dict(dataset="svhn", nz=100, ngf=64, leak=1.0)
+        B = 64
+        args, netG, netF = build_nets(c, DEV, seed=4)
+        x_np, z_np, _ = synth.inputs(B, 100, 3, 32, 1, seed=9)
+        z, x = torch.from_numpy(z_np), torch.from_numpy(x_np)
+        flat, pairs, loss = lsnf_b200.generator_gradients(netG, z.to(DEV), x.to(DEV), B)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in to_torch(synth.generator_state("svhn", 100, 64, 3, seed=4)).items()}
+        layers = refpath.generator_layers("svhn", 100, 64)
+        want = torch.nn.functional.mse_loss(refpath.generator_forward(leaves, z, layers, 1.0), x, reduction="sum") / B
+        want.backward()
+        named = dict(netG.named_parameters())
+        got = {id(p): g for p, g in pairs}
+        errs = {k: rel_l2(got[id(named[k])].cpu(), leaves[k].grad) for k in leaves}
+        print("single-pass data gradient, weight gradients:", ", ".join(f"{k} {e:.1e}" for k, e in errs.items()))
+        assert max(errs.values()) < 2e-3 and errs["gen.9.weight"] < REL_TOL
+    finally:
+        lsnf_b200.clear_plans()
