@@ -57,6 +57,21 @@ static int pick_block_n(int n) {
   return 64;
 }
 
+// Hidden stages whose 256 x 256 CTA-pair tiles would leave more than half of the 74 pairs idle AND whose K loop is
+// short (<= 32 blocks: nothing for the persistent ring to amortise) take 128-wide tiles on the 1-CTA kernel instead,
+// which spreads them over 2-4x as many SMs.  Measured in round 2 (B200): SVHN B=100 forward layer 1 44.6 -> 29.6 us and
+// data gradient of layer 2 41.9 -> 27.5 us (437 k -> 504 k latent-steps/s); with longer K loops (>= 64 blocks: CelebA,
+// the deep HQ256 layers) the same switch LOSES 10-80 us per stage -- the pair kernel halves the weight traffic per
+// CTA -- hence the bound.
+static int pick_block_n_hidden(int n, int rows, int phases, int k_blocks) {
+  const int bn = pick_block_n(n);
+  if (bn != 256 || k_blocks > 32) return bn;
+  const int mtiles = (rows + BLOCK_M - 1) / BLOCK_M;
+  const int pair_tiles = (mtiles + 1) / 2 * (n / 256) * phases;
+  const int small_tiles = mtiles * (n / 128) * phases;
+  return (pair_tiles <= 37 && small_tiles <= 2 * 148) ? 128 : 256;
+}
+
 static void make_box(int hg, int wg, int* bb, int* bh, int* bw) {
   *bw = std::min(wg, BLOCK_M);
   *bh = std::min(hg, BLOCK_M / *bw);
@@ -280,7 +295,11 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
           I.epilogue = EPI_PARTIAL; I.out_channels = I.n_pad;
           I.n_phases = 1; I.out_mul = 1; I.n_taps[0] = 1; I.taps[0][0] = {0, 0, 0, 0};
           p->dlast_pad = I.n_pad;
-        } else { I.n_valid = I.n_pad = y.co; I.block_n = pick_block_n(y.co); I.epilogue = EPI_ACT_HL; }
+        } else {
+          I.n_valid = I.n_pad = y.co; I.epilogue = EPI_ACT_HL;
+          I.block_n = pick_block_n_hidden(y.co, B * y.hin * y.hin, (y.k == 4 && y.s == 2) ? 4 : 1,
+                                          ((y.k == 4 && y.s == 2) ? 4 : y.k * y.k) * (y.ci / BLOCK_K));
+        }
         if (st.last) {
           // taps already set (single centre tap)
         } else if (y.k == 4 && y.s == 2 && y.p == 1) {
@@ -360,7 +379,7 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
         if (!(y.k == 4 && y.s == 2 && y.p == 1)) { delete p; return fail(LSNF_ERR_INVALID, "unsupported hidden layer geometry"); }
         I.grid_h = I.grid_w = y.hin;
         I.k_per_tap = y.co;
-        I.n_valid = I.n_pad = y.ci; I.block_n = pick_block_n(y.ci);
+        I.n_valid = I.n_pad = y.ci; I.block_n = pick_block_n_hidden(y.ci, B * y.hin * y.hin, 1, 16 * (y.co / BLOCK_K));
         I.a_planes = 4;
         I.n_taps[0] = up2_bwd_taps(I.n_pad, I.taps[0]);
         st.a_off = p->off_gpre[l];
