@@ -191,14 +191,15 @@ def assert_updates_agree(got, want, start, lr, steps, what, strict):
     """strict (kink-free generator): element-wise agreement as assert_params_close.  With LeakyReLU kinks the gradient
     itself is only defined up to the sign decisions of near-zero pre-activations (see the gradient test above), and
     Adam turns every element's gradient into a step of size ~lr whatever its magnitude, so element-wise agreement is
-    not a meaningful demand; the two updates must then point the same way (cosine > 0.8) and respect the step bound."""
+    not a meaningful demand; the two updates must then point the same way (cosine > 0.98; measured 0.996 ... 1.000) and
+    respect the step bound."""
     if strict:
         return assert_params_close(got, want, lr, steps, what)
     du, dr = (got - start).flatten().double(), (want - start).flatten().double()
     cos = float((du @ dr) / (du.norm() * dr.norm() + 1e-30))
     d = (got - want).abs()
     print(f"{what}: update cosine {cos:.4f}, max |diff| {float(d.max()):.2e}, fraction above 2e-5: {float((d > 2e-5).float().mean()):.2e}")
-    assert cos > 0.8 and float(d.max()) <= 2.2 * lr * steps, (what, cos)
+    assert cos > 0.98 and float(d.max()) <= 2.2 * lr * steps, (what, cos)
 
 
 @pytest.mark.parametrize("leak", [1.0, 0.2])
