@@ -51,12 +51,12 @@ def test_cifar_headline_shape_multi_seed_against_oracle():
 
 @pytest.mark.parametrize("name,c,B,T", [
     ("svhn", dict(dataset="svhn", nz=100, ngf=64, f_width=64, sigma=0.3), 100, 20),
-    ("celeba_crop", dict(dataset="celeba_crop", nz=100, ngf=128, f_width=64, sigma=0.3), 100, 2),
-    ("celeba_hq256", dict(dataset="celeba_hq256", nz=100, ngf=128, f_width=128, sigma=1.0), 8, 1),
+    ("celeba_crop", dict(dataset="celeba_crop", nz=100, ngf=128, f_width=64, sigma=0.3), 100, 20),
+    ("celeba_hq256", dict(dataset="celeba_hq256", nz=100, ngf=128, f_width=128, sigma=1.0), 8, 20),
 ])
 def test_baseline_configs_at_true_widths_against_oracle(name, c, B, T):
-    # (1b) configs 1, 3, 5 at the channel widths / batch sizes BASELINE.json names (different ngf means different N
-    # tiles, ring geometries and pair / 1-CTA kernel choices than the small fixtures)
+    # (1b) configs 1, 3, 5 exactly as BASELINE.json names them -- channel widths, batch sizes AND the full g_l_steps = 20
+    # chain (different ngf means different N tiles, ring geometries and pair / 1-CTA kernel choices than the fixtures)
     c = dict(c, T=T)
     img = synth.image_size(c["dataset"])
     x_np, z0_np, eps_np = synth.inputs(B, c["nz"], 3, img, T, seed=17)
