@@ -482,7 +482,7 @@ def main():
     dom = max(table, key=lambda t: t["us"])
     step_us = ms_total * 1e3 / (a.steps * R) / T   # one Langevin iteration
     # DRAM traffic of the dominant launch: from the ncu --set full capture of THIS build of the kernels
-    # (tools/run_profiles.sh writes profiles/ncu_dominant_kernel.json with the hash of the CUDA sources); a capture
+    # (tools/run_final.sh writes profiles/ncu_dominant_kernel.json with the hash of the CUDA sources); a capture
     # of other sources is refused
     traffic, traffic_note = None, "no ncu capture under profiles/ for this workload"
     tpath = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, final GPU pass on the final sources: whole GPU suite, smoke, the driver's bench command and the reference
+# final GPU pass on the final sources: whole GPU suite, smoke, the driver's bench command and the reference
 # arm, config 4 in full on one GPU (50 000 latents; one 8 000-iteration call), then the ncu evidence of the same build
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -q -m gpu -s > gpurun_out/t_gpu_final.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/t_gpu_final.log | cut -c1-300

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, third GPU pass: parameter-update tests, the training-iteration bench, and the bench lines of every
+# parameter-update tests, the training-iteration bench, and the bench lines of every
 # BASELINE workload (configs 1-5) plus the saturating-batch CIFAR-10 lines
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_gpu_param_updates.py tests/test_gpu_langevin.py -q -s -x -k "update or iteration or gradients or adam" > gpurun_out/t_gpu_updates.log 2>&1; echo "updates rc=$?"; grep -v "^$" gpurun_out/t_gpu_updates.log | tail -12 | cut -c1-300
