@@ -88,8 +88,8 @@ def workload_config(name, w):
     """The workload keys both arms report under `config` (identical dicts => the driver's same_config check holds)."""
     return {"workload": name, "dataset": w["dataset"], "nz": w["nz"], "ngf": w["ngf"], "f_width": w["f_width"],
             "g_l_steps": w["T"], "batch_per_gpu": w["B"], "g_llhd_sigma": w["sigma"],
-            "l2": "CUDA arm: L2 flushed between timed calls (256 MB written, inside the timed region), per-call working "
-                  "set > 4x L2; reference arm: host CPU, not applicable"}
+            "l2": "CUDA arm: L2 flushed between timed calls (256 MB written, inside the timed region); reference arm: "
+                  "host CPU, not applicable"}
 
 
 class ClockSampler:
