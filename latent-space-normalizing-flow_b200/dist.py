@@ -23,8 +23,9 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 def langevin_sharded(z_global, x_global, netG, netF, args, *, seed: int, rank: int = None, world: int = None,
                      gather: bool = False, **kw):
-    """Run this rank's shard of a global batch.  Noise is keyed by the GLOBAL sample index, so the concatenation
-    over ranks equals the single-GPU result exactly.  Returns (z_shard or gathered z, |grad_g|, |grad_f|)
+    """Run this rank's shard of a global batch.  Noise is keyed by the GLOBAL sample index, so every rank draws
+    exactly the noise the single-GPU run draws for its samples (the latents then agree up to fp32 summation order:
+    split-K / stream-K cut points depend on the tile count).  Returns (z_shard or gathered z, |grad_g|, |grad_f|)
     with the two diagnostics averaged over the global batch when ``gather``."""
     from .langevin import sample_langevin_post_z_with_flow
     rank = dist.get_rank() if rank is None else rank
