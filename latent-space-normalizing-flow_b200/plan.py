@@ -145,7 +145,9 @@ class Plan:
                 keep.append(lad)
                 lad_ptr = C.c_void_p(lad.data_ptr())
                 if need_inverse:
-                    inv = torch.linalg.inv(w_all).contiguous()  # model.py:193 (fp32)
+                    # model.py:193 (fp32).  inv_ex: torch.linalg.inv reads cuSOLVER's status on the HOST (a device
+                    # synchronisation per call, i.e. per training iteration); a singular W gives inf/NaN latents instead
+                    inv = torch.linalg.inv_ex(w_all, check_errors=False).inverse.contiguous()
                     keep.append(inv)
                     winv = _cabi.ptr_array([inv[i].data_ptr() for i in range(len(steps))])
             else:
