@@ -118,7 +118,9 @@ int lsnf_pack_generator_weights(lsnf_plan* plan, const float* const* weights, co
  * third pointer of each step is ignored and perm / perm_inverse hold f_depth device pointers to int32[nz].
  * log_abs_det: DEVICE array [f_depth] of log|det W_i| evaluated in fp64 as model.py:182 does (ignored for shuffle);
  * w_inverse: f_depth device pointers to [nz,nz] inverses (model.py:193), or NULL if lsnf_flow_inverse is
- * not going to be called.  Both are hoisted out of the Langevin loop: parameters are constant during it. */
+ * not going to be called.  Both are hoisted out of the Langevin loop: parameters are constant during it.
+ * log_abs_det == NULL (f_permutation 2, nz <= 160): the library evaluates both itself in one launch (fp64 Gauss-Jordan
+ * with partial pivoting, one CTA per step) and w_inverse is ignored. */
 int lsnf_pack_flow_weights(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                            const int32_t* const* perm_inverse, const float* log_abs_det,
                            const float* const* w_inverse, lsnf_stream stream);

@@ -644,6 +644,115 @@ __global__ void flow_pack_kernel(FlowPackPtrs q, FlowLayout f, float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// log|det W| (fp64, model.py:182) and W^-1 (model.py:193) of every step's invertible 1x1 matrix in ONE launch: one CTA
+// per matrix, in-place Gauss-Jordan elimination with partial pivoting on an fp64 copy in shared memory; the log-abs
+// pivots sum to log|det W|, the result is W^-1 (cast to fp32).  Replaces torch.linalg.det(w.double()) + torch.linalg
+// .inv(w) -- two batched LU factorisations, ~1 ms of small kernels per parameter version -- when the caller passes no
+// log_abs_det to lsnf_pack_flow_weights.  A singular W yields -inf / non-finite entries, as the reference's
+// log(abs(det)) does.
+// ---------------------------------------------------------------------------------------------------
+constexpr int LINALG_THREADS = 512;
+constexpr int LINALG_MAX_N = 160;   // n*n fp64 must fit the 227 KB of shared memory
+
+struct LinalgArgs {
+  const float* w[32];
+  float* winv;      // [depth][n][n]
+  float* logdet;    // [depth]
+  int n;
+};
+
+__global__ void __launch_bounds__(LINALG_THREADS) flow_logdet_inverse_kernel(LinalgArgs a) {
+  extern __shared__ __align__(16) double A[];   // [n][n] row-major
+  __shared__ double rowk[LINALG_MAX_N], colk[LINALG_MAX_N];
+  __shared__ double red_v[LINALG_THREADS / 32];
+  __shared__ int red_i[LINALG_THREADS / 32];
+  __shared__ int piv[LINALG_MAX_N];
+  __shared__ int s_p;
+  const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ W = a.w[blockIdx.x];
+  for (int i = tid; i < n * n; i += LINALG_THREADS) A[i] = (double)W[i];
+  __syncthreads();
+  double logdet = 0.0;   // meaningful in thread 0
+  for (int k = 0; k < n; ++k) {
+    // ---- partial pivoting: row of the largest |A[i][k]|, i >= k (ties: smallest i, deterministic) ----
+    double bv = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += LINALG_THREADS) {
+      const double v = fabs(A[i * n + k]);
+      if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double v = red_v[0];
+      int p = red_i[0];
+      for (int w2 = 1; w2 < LINALG_THREADS / 32; ++w2)
+        if (red_v[w2] > v || (red_v[w2] == v && red_i[w2] < p)) { v = red_v[w2]; p = red_i[w2]; }
+      s_p = p; piv[k] = p;
+      logdet += log(v);
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != k)
+      for (int j = tid; j < n; j += LINALG_THREADS) {
+        const double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t;
+      }
+    __syncthreads();
+    // ---- new pivot row and the old pivot column ----
+    const double pv = A[k * n + k];
+    for (int j = tid; j < n; j += LINALG_THREADS) {
+      rowk[j] = (j == k ? 1.0 : A[k * n + j]) / pv;
+      colk[j] = A[j * n + k];
+    }
+    __syncthreads();
+    // ---- eliminate column k from every other row; row k becomes the scaled pivot row (a warp per row) ----
+    for (int i = warp; i < n; i += LINALG_THREADS / 32) {
+      double* row = A + i * n;
+      if (i == k) {
+        for (int j = lane; j < n; j += 32) row[j] = rowk[j];
+      } else {
+        const double f = colk[i];
+        for (int j = lane; j < n; j += 32) row[j] = (j == k ? 0.0 : row[j]) - f * rowk[j];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- undo the row interchanges: (P W)^-1 = W^-1 P^-1, i.e. swap the columns back in reverse order ----
+  for (int k = n - 1; k >= 0; --k) {
+    const int p = piv[k];
+    if (p != k)
+      for (int i = tid; i < n; i += LINALG_THREADS) {
+        const double t = A[i * n + k]; A[i * n + k] = A[i * n + p]; A[i * n + p] = t;
+      }
+    __syncthreads();
+  }
+  float* out = a.winv + (size_t)blockIdx.x * n * n;
+  for (int i = tid; i < n * n; i += LINALG_THREADS) out[i] = (float)A[i];
+  if (tid == 0) a.logdet[blockIdx.x] = (float)logdet;
+}
+
+int launch_flow_logdet_inverse(const lsnf_plan* plan, const float* const* params, float* winv, float* logdet,
+                               cudaStream_t s) {
+  const int n = plan->cfg.nz, depth = plan->cfg.f_depth;
+  if (n > LINALG_MAX_N || depth > 32) {
+    set_error("built-in log|det W| / W^-1 supports nz <= 160: pass log_abs_det and w_inverse to lsnf_pack_flow_weights");
+    return LSNF_ERR_UNSUPPORTED;
+  }
+  LinalgArgs a;
+  for (int i = 0; i < depth; ++i) a.w[i] = params[i * LSNF_FLOW_PTRS_PER_STEP + 2];
+  a.winv = winv; a.logdet = logdet; a.n = n;
+  flow_logdet_inverse_kernel<<<depth, LINALG_THREADS, (size_t)n * n * sizeof(double), s>>>(a);
+  LSNF_CUDA(cudaGetLastError());
+  return LSNF_OK;
+}
+
 int launch_flow_pack(lsnf_plan* plan, const float* const* params, const int32_t* const* perm,
                      const int32_t* const* perm_inv, const float* log_abs_det, const float* const* winv,
                      cudaStream_t s) {
@@ -746,6 +855,8 @@ int flow_prepare_device(int device) {
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   LSNF_CUDA(cudaFuncSetAttribute(flow_inverse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  LSNF_CUDA(cudaFuncSetAttribute(flow_logdet_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 LINALG_MAX_N * LINALG_MAX_N * (int)sizeof(double)));
   done[device] = true;
   return LSNF_OK;
 }

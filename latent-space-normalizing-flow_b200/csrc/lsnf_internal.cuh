@@ -173,7 +173,7 @@ struct lsnf_plan {
   bool wg_ready = false;                // the forward pass + data-gradient chain of lsnf_generator_param_grads ran
   lsnf::FlowStash fstash;
   lsnf::FlowGradLayout fgrad;
-  size_t off_fstash = 0, off_fgrad = 0, off_floss = 0;
+  size_t off_fstash = 0, off_fgrad = 0, off_floss = 0, off_flinalg = 0;
   // workspace layout (byte offsets)
   size_t ws_bytes = 0;
   size_t off_zhl = 0, off_act[8] = {0}, off_gpre[8] = {0}, off_mbits[8] = {0}, off_xhat = 0, off_im2col = 0, off_partial = 0;
@@ -259,6 +259,8 @@ int launch_flow_inverse(const lsnf_plan* plan, const float* eps, float* z, float
 int launch_adam(int n, float* const* params, const float* const* grads, float* const* m, float* const* v,
                 const int64_t* sizes, const int32_t* grad_kk, const int32_t* grad_inner, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, const float* grad_scale, cudaStream_t s);
+int launch_flow_logdet_inverse(const lsnf_plan* plan, const float* const* params, float* winv, float* logdet,
+                               cudaStream_t s);
 int launch_flow_param_grads(const lsnf_plan* plan, const float* z, float inv_global_batch, float* grads, float* loss,
                             cudaStream_t s);
 int launch_update(const lsnf_plan* plan, float* z, const float* gg, const float* partial, int nsplit, float gscale,

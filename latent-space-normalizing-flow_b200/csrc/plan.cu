@@ -228,6 +228,8 @@ extern "C" int lsnf_plan_create(const lsnf_config* cfg, lsnf_plan** out) {
     t.gl0 = ts(f.nz); t.gl1 = ts(f.w); t.gl2 = ts(f.w); t.gl3 = ts(f.n_out);
     t.layer_floats = so;
     p->off_fstash = take(so * 4 * (size_t)B * c.f_depth);
+    // W^-1 [f_depth][nz][nz] and log|det W| [f_depth] when the library evaluates them itself
+    p->off_flinalg = take(((size_t)c.f_depth * f.nz * f.nz + 32) * 4);
     FlowGradLayout& gl = p->fgrad;
     const size_t sizes[LSNF_FLOW_PTRS_PER_STEP] = {
         (size_t)f.nz, (size_t)f.nz, (size_t)f.nz * f.nz, (size_t)f.half * f.w, (size_t)f.w, (size_t)f.w,
@@ -692,9 +694,20 @@ extern "C" int lsnf_pack_flow_weights(lsnf_plan* plan, const float* const* param
                                       const int32_t* const* perm_inverse, const float* log_abs_det,
                                       const float* const* w_inverse, lsnf_stream stream) {
   if (!plan || !plan->bound) return fail(LSNF_ERR_STATE, "plan not bound");
-  if (!params || (!log_abs_det && plan->cfg.f_permutation == 2)) return fail(LSNF_ERR_INVALID, "null argument");
+  if (!params) return fail(LSNF_ERR_INVALID, "null argument");
   if (plan->cfg.f_permutation == 1 && (!perm || !perm_inverse)) return fail(LSNF_ERR_INVALID, "permutation indices missing");
-  int rc = launch_flow_pack(plan, params, perm, perm_inverse, log_abs_det, w_inverse, (cudaStream_t)stream);
+  int rc;
+  const float* winv_ptrs[32];
+  if (!log_abs_det && plan->cfg.f_permutation == 2) {
+    // the library evaluates log|det W| (fp64) and W^-1 itself: one launch, one CTA per step
+    float* winv = (float*)(plan->ws + plan->off_flinalg);
+    float* ld = winv + (size_t)plan->cfg.f_depth * plan->cfg.nz * plan->cfg.nz;
+    if ((rc = launch_flow_logdet_inverse(plan, params, winv, ld, (cudaStream_t)stream))) return rc;
+    for (int i = 0; i < plan->cfg.f_depth; ++i) winv_ptrs[i] = winv + (size_t)i * plan->cfg.nz * plan->cfg.nz;
+    log_abs_det = ld;
+    w_inverse = winv_ptrs;
+  }
+  rc = launch_flow_pack(plan, params, perm, perm_inverse, log_abs_det, w_inverse, (cudaStream_t)stream);
   if (rc) return rc;
   plan->f_packed = true;
   plan->have_winv = (w_inverse != nullptr) || plan->cfg.f_permutation == 1;

@@ -38,44 +38,50 @@ class FusedAdam(torch.optim.Adam):
         weight (``grad_inner[i]`` = C_out).  ``grad_scale``: 0-d CUDA tensor multiplied into every gradient (norm
         clipping).  Hyper-parameters come from the parameter group each tensor belongs to."""
         lib = _cabi.load()
-        group_of = {}
-        for gi, g in enumerate(self.param_groups):
-            if g.get("amsgrad") or g.get("maximize"):
-                raise NotImplementedError("FusedAdam.fused_step: amsgrad / maximize are not used by the reference")
-            for p in g["params"]:
-                group_of[id(p)] = gi
-        by_group = {}
-        for i, p in enumerate(params):
-            if id(p) not in group_of:
-                raise ValueError("parameter does not belong to this optimizer")
-            by_group.setdefault(group_of[id(p)], []).append(i)
-        for gi, idxs in by_group.items():
-            g = self.param_groups[gi]
-            steps = set()
-            ptr_p, ptr_g, ptr_m, ptr_v, sizes, kk, inner = [], [], [], [], [], [], []
-            for i in idxs:
-                p, gr = params[i], grads[i]
-                if not (p.is_cuda and gr.is_cuda and p.dtype == torch.float32 and gr.dtype == torch.float32
-                        and p.is_contiguous() and gr.is_contiguous() and gr.numel() == p.numel()):
+        key = tuple(id(p) for p in params)
+        cached = getattr(self, "_fused_groups", {}).get(key)
+        if cached is None:   # first use of this parameter set: group lookup and tensor validation, done once
+            group_of = {}
+            for gi, g in enumerate(self.param_groups):
+                if g.get("amsgrad") or g.get("maximize"):
+                    raise NotImplementedError("FusedAdam.fused_step: amsgrad / maximize are not used by the reference")
+                for p in g["params"]:
+                    group_of[id(p)] = gi
+            by_group = {}
+            for i, p in enumerate(params):
+                if id(p) not in group_of:
+                    raise ValueError("parameter does not belong to this optimizer")
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise RuntimeError("FusedAdam.fused_step needs contiguous float32 CUDA parameters and gradients")
-                st = self._ensure_state(p)
-                st["step"] += 1
-                steps.add(int(st["step"].item()))
-                ptr_p.append(p.data_ptr()); ptr_g.append(gr.data_ptr())
-                ptr_m.append(st["exp_avg"].data_ptr()); ptr_v.append(st["exp_avg_sq"].data_ptr())
-                sizes.append(p.numel())
-                kk.append(int(grad_kk[i]) if grad_kk is not None else 1)
-                inner.append(int(grad_inner[i]) if grad_inner is not None else 1)
-            if len(steps) != 1:
+                by_group.setdefault(group_of[id(p)], []).append(i)
+            cached = list(by_group.items())
+            if not hasattr(self, "_fused_groups"):
+                self._fused_groups = {}
+            self._fused_groups[key] = cached
+        for gi, idxs in cached:
+            g = self.param_groups[gi]
+            states = [self._ensure_state(params[i]) for i in idxs]
+            step_tensors = [st["step"] for st in states]
+            torch._foreach_add_(step_tensors, 1)
+            step = int(step_tensors[0].item())
+            if int(step_tensors[-1].item()) != step:
                 raise RuntimeError("FusedAdam.fused_step: parameters of one group are at different step counts")
             n = len(idxs)
+            for i in idxs:
+                gr = grads[i]
+                if not (gr.is_cuda and gr.dtype == torch.float32 and gr.is_contiguous() and gr.numel() == params[i].numel()):
+                    raise RuntimeError("FusedAdam.fused_step needs contiguous float32 CUDA parameters and gradients")
+            ptr = C.c_void_p * n
             dev = params[idxs[0]].device
             with torch.cuda.device(dev):
                 _cabi.check(lib.lsnf_adam_step(
-                    n, _cabi.ptr_array(ptr_p), _cabi.ptr_array(ptr_g), _cabi.ptr_array(ptr_m), _cabi.ptr_array(ptr_v),
-                    (C.c_int64 * n)(*sizes), (C.c_int32 * n)(*kk), (C.c_int32 * n)(*inner),
+                    n, ptr(*[params[i].data_ptr() for i in idxs]), ptr(*[grads[i].data_ptr() for i in idxs]),
+                    ptr(*[st["exp_avg"].data_ptr() for st in states]), ptr(*[st["exp_avg_sq"].data_ptr() for st in states]),
+                    (C.c_int64 * n)(*[params[i].numel() for i in idxs]),
+                    (C.c_int32 * n)(*[int(grad_kk[i]) if grad_kk is not None else 1 for i in idxs]),
+                    (C.c_int32 * n)(*[int(grad_inner[i]) if grad_inner is not None else 1 for i in idxs]),
                     float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                    float(g["weight_decay"]), steps.pop(),
+                    float(g["weight_decay"]), step,
                     C.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else None,
                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "lsnf_adam_step")
         bump_versions(params)

@@ -15,6 +15,15 @@ _FLOW_PARAM_ORDER = ("actnorm.b", "actnorm.logs", "invertible_1x1_conv.w", "f.fc
                      "f.fc_zeros.b", "f.fc_zeros.logs")
 
 
+def flow_step_params(st):
+    """The twelve parameter tensors of one ``revnet2d_step`` in the order of ``_FLOW_PARAM_ORDER`` (plain attribute
+    access: this runs once per training iteration); ``None`` for the 1x1 matrix of a shuffle step."""
+    f = st.f
+    w = st.invertible_1x1_conv.w if st.invertible_1x1_conv is not None else None
+    return [st.actnorm.b, st.actnorm.logs, w, f.fc_1.w, f.fc_1.actnorm.b, f.fc_1.actnorm.logs, f.fc_2.w,
+            f.fc_2.actnorm.b, f.fc_2.actnorm.logs, f.fc_zeros.w, f.fc_zeros.b, f.fc_zeros.logs]
+
+
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -123,12 +132,10 @@ class Plan:
         steps = netF.revnet2d_s[0].revnet2d_step_s
         named = []
         for st in steps:
-            sd = dict(st.named_parameters())
-            for k in _FLOW_PARAM_ORDER:
-                if k == "invertible_1x1_conv.w" and self.f_permutation != 2:
-                    named.append(sd["actnorm.b"])  # placeholder pointer, ignored by the library
-                else:
-                    named.append(sd[k])
+            ps = flow_step_params(st)
+            if ps[2] is None:
+                ps[2] = ps[0]  # placeholder pointer for the absent 1x1 matrix, ignored by the library
+            named += ps
         sig = self._sig(named)
         if sig == self._f_sig and (self._f_has_inv or not need_inverse):
             return
@@ -138,7 +145,11 @@ class Plan:
             params = _cabi.ptr_array([t.data_ptr() for t in named])
             keep = []
             perm = perm_inv = lad_ptr = winv = None
-            if self.f_permutation == 2:
+            if self.f_permutation == 2 and self.nz <= 160:
+                # log|det W| (fp64, model.py:182) and W^-1 (model.py:193) by the library's own kernel: one launch
+                # instead of two batched torch LU factorisations (~1 ms of small kernels per parameter version)
+                need_inverse = True
+            elif self.f_permutation == 2:
                 w_all = torch.stack([st.invertible_1x1_conv.w.detach() for st in steps])
                 # model.py:182 -- determinant in fp64, cast back to fp32; hoisted out of the loop
                 lad = torch.log(torch.abs(torch.linalg.det(w_all.double()))).float().contiguous()

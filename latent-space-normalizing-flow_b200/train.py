@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 from .langevin import sample_langevin_post_z_with_flow
 from .optim import FusedAdam
-from .plan import _FLOW_PARAM_ORDER
+from .plan import flow_step_params
 
 
 def make_optimizers(netG, netF, args):
@@ -131,18 +131,17 @@ def flow_params_in_order(netF):
     tensors of ``_FLOW_PARAM_ORDER``; ``None`` where a step has no such parameter (shuffle permutation)."""
     out = []
     for st in netF.revnet2d_s[0].revnet2d_step_s:
-        sd = dict(st.named_parameters())
-        for k in _FLOW_PARAM_ORDER:
-            out.append(sd.get(k) if not (k == "invertible_1x1_conv.w" and netF.f_permutation != 2) else None)
+        out += flow_step_params(st)
     return out
 
 
-def flow_gradients(netF, z_k, global_batch):
+def flow_gradients(netF, z_k, global_batch, plan=None):
     """(flat gradient buffer, [(parameter, gradient view)], this rank's share of loss_f) of
     loss_f = -(1/global_batch) sum_b log p(z_b) (train.py:403-410) through ``lsnf_flow_param_grads``."""
     b = z_k.shape[0]
     z2 = z_k.detach().reshape(b, netF.nz).contiguous().float()
-    plan = netF._plan(b, z2.device)
+    if plan is None:
+        plan = netF._plan(b, z2.device)
     plan.ensure_flow(netF, need_inverse=True)
     flat = getattr(plan, "_fgrad_flat", None)
     if flat is None:
@@ -154,12 +153,12 @@ def flow_gradients(netF, z_k, global_batch):
     return flat, pairs, loss
 
 
-def flow_update(netF, optF, z_k, args, *, global_batch=None, group=None, world=1):
+def flow_update(netF, optF, z_k, args, *, global_batch=None, group=None, world=1, plan=None):
     """The flow step of train.py:403-415 without autograd: gradients by the fused flow kernel + batch reductions,
     one all-reduce of the flat buffer across ranks, optional norm clipping, fused Adam.  Returns loss_f."""
     g = lambda k, d: args.get(k, d) if isinstance(args, dict) else getattr(args, k, d)
     b_global = z_k.shape[0] if global_batch is None else int(global_batch)
-    flat, pairs, loss = flow_gradients(netF, z_k, b_global)
+    flat, pairs, loss = flow_gradients(netF, z_k, b_global, plan=plan)
     if world > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
@@ -231,6 +230,6 @@ def training_iteration(x, netG, netF, optG, optF, args, *, global_batch=None, sa
     # ... overlapped with the flow update (train.py:403-415): gradient kernels + one flat all-reduce + fused Adam.
     # The two updates are independent (neither reads the other network's parameters), so finishing the generator's
     # Adam step after the flow's changes nothing.
-    loss_f = flow_update(netF, optF, z_k, args, global_batch=b_global, group=group, world=world)
+    loss_f = flow_update(netF, optF, z_k, args, global_batch=b_global, group=group, world=world, plan=plan)
     loss_g = pending.finish()
     return loss_g.detach(), loss_f.detach(), gn, fn, z_k
