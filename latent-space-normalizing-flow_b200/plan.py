@@ -4,6 +4,7 @@ streams only."""
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -100,7 +101,16 @@ class Plan:
     # ---- parameters ----------------------------------------------------------------------------------
     @staticmethod
     def _sig(tensors):
-        return tuple((t.data_ptr(), t._version) for t in tensors)
+        """What the packed copies were made from: the Parameter OBJECTS (weakly referenced), their storage and their
+        version counters.  Storage address + version alone is not an identity: the caching allocator hands the
+        addresses of a freed model to the next one, whose freshly loaded parameters carry the same versions -- a
+        second model built after the first one was dropped would silently run on the first one's packed weights."""
+        return tuple((weakref.ref(t), t.data_ptr(), t._version) for t in tensors)
+
+    @staticmethod
+    def _same(sig, tensors) -> bool:
+        return sig is not None and len(sig) == len(tensors) and all(
+            r() is t and ptr == t.data_ptr() and ver == t._version for (r, ptr, ver), t in zip(sig, tensors))
 
     def invalidate(self) -> None:
         """Forget the packed parameters: the next call re-packs the generator and flow weights (and re-evaluates the
@@ -115,9 +125,9 @@ class Plan:
         convs = [m for m in netG.gen if isinstance(m, torch.nn.ConvTranspose2d)]
         ws = [m.weight for m in convs]
         bs = [m.bias for m in convs]
-        sig = self._sig(ws + bs)
-        if sig == self._g_sig:
+        if self._same(self._g_sig, ws + bs):
             return
+        sig = self._sig(ws + bs)
         for i, (w, b) in enumerate(zip(ws, bs)):
             _check_tensor(w.data, f"gen.{3 * i}.weight", self.device)
             _check_tensor(b.data, f"gen.{3 * i}.bias", self.device)
@@ -136,9 +146,9 @@ class Plan:
             if ps[2] is None:
                 ps[2] = ps[0]  # placeholder pointer for the absent 1x1 matrix, ignored by the library
             named += ps
-        sig = self._sig(named)
-        if sig == self._f_sig and (self._f_has_inv or not need_inverse):
+        if self._same(self._f_sig, named) and (self._f_has_inv or not need_inverse):
             return
+        sig = self._sig(named)
         for t in named:
             _check_tensor(t.data, "flow parameter", self.device)
         with torch.cuda.device(self.device), torch.no_grad():

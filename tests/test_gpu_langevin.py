@@ -294,3 +294,26 @@ def test_training_iteration_runs_and_lowers_the_reconstruction_loss():
     netG.train()
     b = netG(z).detach()
     assert rel_err(a.cpu(), b.cpu()) < 1e-3
+
+
+def test_a_second_model_at_recycled_addresses_is_repacked():
+    # The packed copies of the parameters are cached per plan.  Dropping a model and building another one of the same
+    # shape hands the new parameters the OLD device addresses (caching allocator) with the same version counters:
+    # the plan must still notice that these are different Parameter objects and re-pack (regression: it keyed on
+    # address + version only and silently kept the first model's flow weights).
+    import gc
+    from helpers import build_nets, oracle_langevin
+    c = dict(dataset="svhn", nz=100, ngf=32, sigma=0.3, T=5)
+    x_np, z0_np, eps_np = synth.inputs(8, 100, 3, 32, 5, seed=41)
+    z0, x, eps = (torch.from_numpy(a).to(DEV) for a in (z0_np, x_np, eps_np))
+    args, netG, netF = build_nets(c, DEV, seed=1)
+    lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, eps=eps)
+    old = {p.data_ptr() for p in list(netG.parameters()) + list(netF.parameters())}
+    del netG, netF
+    gc.collect()
+    args, netG, netF = build_nets(c, DEV, seed=2)
+    reused = sum(p.data_ptr() in old for p in list(netG.parameters()) + list(netF.parameters()))
+    z, _, _ = lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, eps=eps)
+    zr, _, _ = oracle_langevin(c, x_np, z0_np, eps_np, seed=2)
+    print(f"{reused} parameter tensors of the second model sit at addresses of the first one")
+    assert rel_l2(z.cpu(), zr) < REL_TOL
