@@ -34,7 +34,7 @@ FLOW=1 timeout 900 ncu --set full --clock-control none -k "regex:flow_forward_ke
 echo "ncu flow rc=$?"
 python tools/ncu_summarize.py gpurun_out/prof_r2_flow.ncu-rep gpurun_out/r2_ncu_full_flow.json; rm -f gpurun_out/prof_r2_flow.ncu-rep
 timeout 300 python tools/prof_train.py > gpurun_out/plain_prof_train.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none -k "regex:tapgemm_tc_kernel|transpose_hl|wgrad_finalize|bias_rowsum|flow_param_grad|adam_kernel|mse_sum" -s 30 -c 40 -f -o gpurun_out/prof_r2_train python tools/prof_train.py > gpurun_out/ncu_train.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k "regex:tapgemm_tc_kernel|transpose_hl|wgrad_finalize|bias_rowsum|flow_param_grad|flow_logdet_inverse|flow_forward_kernel|adam_kernel|mse_sum" -s 30 -c 40 -f -o gpurun_out/prof_r2_train python tools/prof_train.py > gpurun_out/ncu_train.log 2>&1
 echo "ncu train rc=$?"
 python tools/ncu_summarize.py gpurun_out/prof_r2_train.ncu-rep gpurun_out/r2_ncu_full_param_updates.json; rm -f gpurun_out/prof_r2_train.ncu-rep
 du -sh gpurun_out
