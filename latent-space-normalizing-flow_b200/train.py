@@ -1,9 +1,11 @@
 """One training iteration of the reference (train.py:376-415) on the CUDA path, with data parallelism over the
-latent batch: Langevin posterior inference (``lsnf_langevin_run``), the flow parameter update (``flow_update``:
-``lsnf_flow_param_grads`` + fused Adam) and the generator parameter update.  Each rank
-infers the latents of its shard (no collective) and computes its share of the parameter gradients into ONE flat
-buffer per network, which is summed across ranks with a single all-reduce (NCCL over NVLink) before the fused Adam
-step.
+latent batch: Langevin posterior inference (``lsnf_langevin_run``), the generator parameter update
+(``generator_update``: ``lsnf_generator_param_grads`` -- forward, data-gradient chain, weight-gradient tap-GEMMs -- +
+fused Adam) and the flow parameter update (``flow_update``: ``lsnf_flow_param_grads`` +
+fused Adam; rank 2), all on ONE plan.  Each rank infers the latents of its shard (no collective) and computes its share
+of the parameter gradients into one flat buffer per network; the buffers are summed across ranks (NCCL over NVLink) --
+the generator's layer by layer on a comm stream, overlapping the remaining gradient kernels -- before the fused Adam
+steps.
 """
 from __future__ import annotations
 
