@@ -259,6 +259,8 @@ __global__ void __launch_bounds__(256) last_fused_kernel(const float* __restrict
                                                          int p, int n_pad, int TR, int TC, float seed_scale, int fp16,
                                                          int write_lo) {
   extern __shared__ float fs[];
+  pdl_wait();      // the last forward layer's per-tap products must be complete (no-op without the launch attribute)
+  pdl_trigger();
   constexpr int T = (K + S - 1) / S;
   const int tiles_c = (hin + TC - 1) / TC, tiles_r = (hin + TR - 1) / TR;
   const int tc = blockIdx.x % tiles_c, tr = (blockIdx.x / tiles_c) % tiles_r, b = blockIdx.x / (tiles_c * tiles_r);
@@ -393,15 +395,13 @@ int launch_last_fused(const lsnf_plan* plan, const float* x, float seed_scale, c
   uint16_t* a = (uint16_t*)(plan->ws + plan->off_im2col);
   const int one = plan->cfg.bwd_passes == 1 ? 1 : 0;
   if (smem > 160 * 1024) { set_error("fused last-layer kernel: tile does not fit shared memory"); return LSNF_ERR_INVALID; }
+  const dim3 grid(plan->cfg.batch * tiles), block(256);
   if (y.k == 3 && y.s == 1)
-    last_fused_kernel<3, 1><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
-                                                                      plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      seed_scale, one, !one);
+    LSNF_CUDA(launch_k(last_fused_kernel<3, 1>, grid, block, smem, s, d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
+                       plan->img, y.hin, y.p, n_pad, TR, TC, seed_scale, one, !one));
   else
-    last_fused_kernel<4, 2><<<plan->cfg.batch * tiles, 256, smem, s>>>(d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
-                                                                      plan->img, y.hin, y.p, n_pad, TR, TC,
-                                                                      seed_scale, one, !one);
-  LSNF_CUDA(cudaGetLastError());
+    LSNF_CUDA(launch_k(last_fused_kernel<4, 2>, grid, block, smem, s, d, bias, x, xh, a, plan->cfg.batch, plan->cfg.nc,
+                       plan->img, y.hin, y.p, n_pad, TR, TC, seed_scale, one, !one));
   return LSNF_OK;
 }
 
@@ -464,6 +464,8 @@ __global__ void __launch_bounds__(256) langevin_update_kernel(
     const uint64_t* __restrict__ dyn, float* __restrict__ norm_scratch, unsigned int* __restrict__ ticket,
     float* __restrict__ gnorms) {
   __shared__ float4 part[8][64];
+  pdl_wait();      // launched without the attribute (it joins the flow prior's stream): returns at once
+  pdl_trigger();   // the next iteration's first layer may set itself up while this kernel runs
   if (dyn) { seed = dyn[0]; sample_offset = dyn[1]; step_idx += (uint32_t)dyn[2]; }   // per-call values of a replayed CUDA graph
   __shared__ float red[2][256];
   __shared__ bool is_last;

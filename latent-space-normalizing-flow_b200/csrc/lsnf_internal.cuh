@@ -233,11 +233,44 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::lsnf::cuda_fail(e__, #call); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) inside the Langevin loop ----
+// Every kernel of the loop calls pdl_wait() before its first access to global memory (it returns at once unless the
+// launch carried the attribute below, in which case it returns when the stream predecessor has completed and its
+// writes are visible) and then pdl_trigger(), which lets the NEXT kernel's CTAs become resident as soon as every CTA
+// of this grid has got that far: the next launch and its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) then overlap this kernel's body instead of following its last CTA.  Nothing is written to global memory
+// before pdl_wait(), so there is no write-after-read hazard with the predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Set by the loop (plan.cu) around a launch that may start before its stream predecessor has completed; thread-local
+// because plans are driven from several host threads.  Every other launch of the library leaves it 0.
+extern thread_local int g_launch_pdl;
+struct PdlScope {
+  explicit PdlScope(bool on) { g_launch_pdl = on ? 1 : 0; }
+  ~PdlScope() { g_launch_pdl = 0; }
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  if (g_launch_pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernels / launchers implemented in the other translation units
 int launch_tapgemm_simt(const StageHost& st, cudaStream_t s);
 int launch_tapgemm_tc(const StageHost& st, cudaStream_t s);
 int tc_encode_maps(lsnf_plan* plan, StageHost& st);
 void tc_launch_info(const StageHost& st, int num_sms, lsnf_launch_info* out);
+bool tc_stage_is_pair(const StageHost& st);   // the stage runs on the persistent CTA-pair kernel
 int launch_pack_stage(const lsnf_plan* plan, const StageHost& st, const float* w, cudaStream_t s);
 int launch_split_z(const lsnf_plan* plan, const float* z, cudaStream_t s);
 int launch_weight_scales(const lsnf_plan* plan, const float* const* weights, cudaStream_t s);

@@ -7,8 +7,13 @@
 
 #include "lsnf_internal.cuh"
 
+#ifndef LSNF_PDL_DEFAULT
+#define LSNF_PDL_DEFAULT 1
+#endif
+
 namespace lsnf {
 
+thread_local int g_launch_pdl = 0;   // see lsnf_internal.cuh
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -962,6 +967,22 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
   float* z = (float*)(plan->ws + plan->off_z);
   float* gf = (float*)(plan->ws + plan->off_gradf);
   const float* partial = (const float*)(plan->ws + plan->off_partial);
+  // Programmatic dependent launch across the kernel boundaries of the loop's main stream (lsnf_internal.cuh).
+  // LSNF_PDL: 0 off, 1 every boundary, 2 only boundaries with no CTA-pair kernel on either side, 3 / 4 not into / not
+  // out of a CTA-pair kernel.  The update kernel is never launched this way (it also waits for the flow prior's
+  // stream), nor is the first kernel of a call or of a captured graph (no kernel precedes it there).
+  static const int pdl_mode = [] { const char* e = getenv("LSNF_PDL"); return e ? atoi(e) : LSNF_PDL_DEFAULT; }();
+  const bool tc_path = c.gemm_impl == LSNF_GEMM_TCGEN05;
+  bool prev_pair = false, have_prev = false;
+  auto pdl_ok = [&](bool this_pair) {
+    bool ok = tc_path && have_prev && pdl_mode != 0;
+    if (pdl_mode == 2) ok = ok && !this_pair && !prev_pair;
+    if (pdl_mode == 3) ok = ok && !this_pair;
+    if (pdl_mode == 4) ok = ok && !prev_pair;
+    have_prev = true;
+    prev_pair = this_pair;
+    return ok;
+  };
   for (int t = 0; t < steps; ++t) {
     tr.on = trace_env == 1 && t == 1 && !dyn;
     tr.mark("start");
@@ -977,13 +998,22 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
         if ((rc = launch_flow_forward(plan, z, nullptr, nullptr, nullptr, gf, plan->side))) return rc;
         LSNF_CUDA(cudaEventRecord(plan->ev_join, plan->side));
       }
-      if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
+      {
+        PdlScope pdl(pdl_ok(tc_path && tc_stage_is_pair(plan->stages[l])));
+        if ((rc = run_stage(plan, plan->stages[l], s))) return rc;
+      }
       tr.mark(("forward layer " + std::to_string(l)).c_str());
     }
-    if ((rc = launch_last_fused(plan, x, sigma_seed_scale(sigma), s))) return rc;
+    {
+      PdlScope pdl(pdl_ok(false));
+      if ((rc = launch_last_fused(plan, x, sigma_seed_scale(sigma), s))) return rc;
+    }
     tr.mark("gather + tanh + recon grad + im2col");
     for (int i = plan->n_layers; i < 2 * plan->n_layers; ++i) {
-      if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+      {
+        PdlScope pdl(pdl_ok(tc_path && tc_stage_is_pair(plan->stages[i])));
+        if ((rc = run_stage(plan, plan->stages[i], s))) return rc;
+      }
       tr.mark(("dgrad layer " + std::to_string(plan->stages[i].layer)).c_str());
     }
     LSNF_CUDA(cudaStreamWaitEvent(s, plan->ev_join, 0));
@@ -992,6 +1022,7 @@ static int langevin_loop(lsnf_plan* plan, const float* x, int steps, float step_
     if ((rc = launch_update(plan, z, nullptr, partial, plan->ksplit_first, gscale, gf, step_size, e, with_noise, seed,
                             sample_offset, (uint32_t)t, dyn, t == steps - 1 ? gnorms : nullptr, 1, s)))
       return rc;
+    prev_pair = false;   // the update kernel precedes the next iteration's first layer
     tr.mark("update");
     tr.report();
   }

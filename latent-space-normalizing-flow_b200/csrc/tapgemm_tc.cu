@@ -381,6 +381,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched shared / tensor memory only; operands, sign bits and scales are read below
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     {
@@ -828,6 +831,8 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync_all();   // the peer's barriers are initialised before anything can arrive on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();      // see lsnf_internal.cuh: the set-up above overlaps the tail of the previous kernel
+  pdl_trigger();
 
   if (warp == 0) {
     {
@@ -994,6 +999,8 @@ static bool use_pair(const StageHost& sh) {
          (mtiles >= 2 || total >= 8);
 }
 
+bool tc_stage_is_pair(const StageHost& sh) { return use_pair(sh); }
+
 // Ring of the 1-CTA kernel for one launch: stage bytes, depth, dynamic shared memory to request.
 struct RingGeom { int nst; size_t stage_bytes, smem; };
 static RingGeom ring_geometry(const StageDev& d) {
@@ -1128,8 +1135,7 @@ static int launch_bn(const StageHost& sh, cudaStream_t s) {
   const RingGeom g = ring_geometry(st);
   st.nst = g.nst;
   dim3 grid(st.tiles_b * st.tiles_h * st.tiles_w, st.n_pad / BN, (st.wgrad ? st.ph[0].ntaps : st.nphase) * st.ksplit);
-  tapgemm_tc_kernel<BN><<<grid, TC_THREADS, g.smem, s>>>(sh.tmA, sh.tmB, sh.tmO, st);
-  LSNF_CUDA(cudaGetLastError());
+  LSNF_CUDA(launch_k(tapgemm_tc_kernel<BN>, grid, dim3(TC_THREADS), g.smem, s, sh.tmA, sh.tmB, sh.tmO, st));
   return LSNF_OK;
 }
 
@@ -1159,10 +1165,9 @@ static int launch_pair(const StageHost& sh, cudaStream_t s) {
   const int pairs = launch_st.sk_enable ? max_pairs : std::min(num_tiles, max_pairs);
   dim3 grid(2 * pairs, 1, 1);
   if (st.passes == 1)
-    tapgemm_tc2_kernel<true><<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
+    LSNF_CUDA(launch_k(tapgemm_tc2_kernel<true>, grid, dim3(TC_THREADS), P_SMEM_BYTES, s, sh.tmA, sh.tmB, sh.tmO, launch_st));
   else
-    tapgemm_tc2_kernel<false><<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(sh.tmA, sh.tmB, sh.tmO, launch_st);
-  LSNF_CUDA(cudaGetLastError());
+    LSNF_CUDA(launch_k(tapgemm_tc2_kernel<false>, grid, dim3(TC_THREADS), P_SMEM_BYTES, s, sh.tmA, sh.tmB, sh.tmO, launch_st));
   return LSNF_OK;
 }
 
