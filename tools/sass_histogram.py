@@ -3,7 +3,8 @@
 Runs `cuobjdump -sass` on latent-space-normalizing-flow_b200/_lib/liblsnf_b200.so and counts, per kernel, the SASS
 mnemonics that prove which hardware paths a kernel uses (B200_PROFILING.md): UTCHMMA (tcgen05.mma), UTCHMMA.2CTA
 (cta_group::2), LDTM / STTM (tcgen05.ld / st: TMEM), UTMALDG / UTMASTG (TMA tensor loads / stores), UBLKCP (bulk
-copies), SYNCS (mbarrier), plus the classic HMMA / FFMA counts for contrast."""
+copies), SYNCS (mbarrier), ACQBULK / PREEXIT (griddepcontrol.wait / launch_dependents: programmatic dependent
+launch), plus the classic HMMA / FFMA counts for contrast."""
 import collections
 import json
 import os
@@ -14,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "latent-space-normalizing-flow_b200", "_lib", "liblsnf_b200.so")
 WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "SYNCS", "ELECT",
-         "HMMA", "FFMA", "MUFU", "BAR.SYNC", "LDG", "STG", "LDS", "STS", "RED", "ATOM"]
+         "ACQBULK", "PREEXIT", "HMMA", "FFMA", "MUFU", "BAR.SYNC", "LDG", "STG", "LDS", "STS", "RED", "ATOM"]
 
 
 def main():
