@@ -155,3 +155,39 @@ def test_two_devices_in_one_process():
                                                                  netG, netF, args, seed=4)
         outs.append(z.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+_PDL_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import lsnf_b200
+from lsnf_b200 import synth
+from helpers import build_nets
+c = dict(dataset="svhn", nz=100, ngf=64, f_width=64, sigma=0.3, T=20)
+x_np, z0_np, _ = synth.inputs(100, 100, 3, 32, 1, seed=21)
+args, netG, netF = build_nets(c, "cuda:0", seed=3)
+z0, x = torch.from_numpy(z0_np).to("cuda:0"), torch.from_numpy(x_np).to("cuda:0")
+outs = [lsnf_b200.sample_langevin_post_z_with_flow(z0, x, netG, netF, args, seed=9)[0].cpu().numpy() for _ in range(2)]
+np.save({out!r}, np.stack(outs))   # [eager first call, graph replay]
+"""
+
+
+def test_programmatic_dependent_launch_changes_no_bit(tmp_path):
+    # DESIGN.md 4.7: the kernels of the loop chain by programmatic dependent launch (LSNF_PDL, read once per process).
+    # It moves launches and kernel set-up earlier and nothing else, so processes with it on (the default: every
+    # boundary), off and restricted around the CTA-pair kernels must produce the same bits -- at SVHN's true width and
+    # batch, where the loop mixes 1-CTA, CTA-pair / stream-K and CUDA-core kernels, eagerly and from the replayed graph.
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = {}
+    for mode in ("0", "1", "2"):
+        out = str(tmp_path / f"z_pdl{mode}.npy")
+        env = dict(os.environ, LSNF_PDL=mode)
+        subprocess.run([sys.executable, "-c", _PDL_SCRIPT.format(root=root, tests=os.path.join(root, "tests"), out=out)],
+                       check=True, env=env, timeout=600)
+        got[mode] = np.load(out)
+        assert np.isfinite(got[mode]).all()
+        assert np.array_equal(got[mode][0], got[mode][1])        # eager == replay within one process
+    assert np.array_equal(got["0"], got["1"]) and np.array_equal(got["0"], got["2"])
