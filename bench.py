@@ -519,7 +519,7 @@ def main():
         json.dump({"stages": table, "flow_prior_kernel_us": flow_us, "iteration_us": step_us}, open(a.stage_table, "w"), indent=1)
 
     cpu_b = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:   # the contract: rank 0, N=1 only (at N>1 the other ranks have left already)
         cpu_T = {"svhn": 10, "cifar10": 2, "celeba_crop": 2, "celeba_hq256": 1, "svhn_test": 10}[a.workload]
         cb = REF_SAMPLE_B.get(a.workload, B)
         rate, dt, threads, done = oracle_rate(w, gsd, fsd, cpu_T, min_seconds=12.0, batch=cb)
