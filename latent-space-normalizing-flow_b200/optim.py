@@ -84,4 +84,5 @@ class FusedAdam(torch.optim.Adam):
                     float(g["weight_decay"]), step,
                     C.c_void_p(grad_scale.data_ptr()) if grad_scale is not None else None,
                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "lsnf_adam_step")
+        self._opt_called = True   # what torch's LR schedulers look at to tell "scheduler stepped before the optimizer"
         bump_versions(params)
