@@ -18,6 +18,12 @@ output directory).  What runs:
   eps -> F^-1 -> G -> [0,1] (train.py:565-586), and with ``--testing_reconstruct`` report the reconstruction error of
   ``g_l_steps * 20`` noise-free Langevin iterations per batch (train.py:606, :641-662).
 
+Status: written in the last session of round 2 after the GPU budget was spent -- the host side (flags, network
+construction, checkpoints, the no-GPU error) is covered by tests/test_example_cli.py on the CPU; the GPU legs have NOT
+been executed on a B200.  They only call entry points that the GPU suite exercises with the same arguments
+(``training_iteration``: tests/test_gpu_langevin.py, tools/train_ddp_check.py; ``sample_x`` / ``reconstruction_error``:
+tests/test_gpu_langevin.py, tests/test_gpu_sampling_and_long_chains.py).
+
 Datasets, FID and image dumps are outside the path this repository rebuilds: images are
 x ~ U(-1, 1), as in bench.py.  There is no CPU fallback: without a CUDA device the script stops with an error.
 """
