@@ -215,11 +215,38 @@ REF_SAMPLE_T = {"svhn": 20, "cifar10": 4, "celeba_crop": 4, "celeba_hq256": 2, "
 REF_SAMPLE_B = {"svhn_test": 100}   # the reference's test loader uses batches of 100 (train.py:598)
 
 
+def oracle_update_seconds(w, gsd, fsd, batch, threads=None, repeats=2):
+    """Seconds of ONE generator step + flow step of train.py:390-415 (autograd + torch.optim.Adam, restated by
+    oracle/refpath.parameter_updates) on the host cores, best of `repeats` after a warm-up.  Baseline legs only."""
+    from oracle import refpath
+    from lsnf_b200 import synth
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    gp = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in gsd.items()}
+    fp = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in fsd.items()}
+    fkeys = refpath.trainable_flow_keys(fp)
+    for k in fkeys:
+        fp[k] = fp[k].clone().requires_grad_(True)
+    adam = lambda ps: torch.optim.Adam(ps, lr=0.0004, weight_decay=0, betas=(0.5, 0.999))   # train.py:294-295
+    optG, optF = adam(list(gp.values())), adam([fp[k] for k in fkeys])
+    layers = refpath.generator_layers(w["dataset"], w["nz"], w["ngf"])
+    x, z, _ = synth.inputs(batch, w["nz"], 3, w["img"], 1, seed=1)
+    x, z = torch.from_numpy(x), torch.from_numpy(z)
+    best = float("inf")
+    for i in range(repeats + 1):
+        t0 = time.perf_counter()
+        refpath.parameter_updates(gp, fp, z, x, layers, optG, optF, depth=5)
+        if i:
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
 def run_reference(a, w, rank, out):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure
     Python/torch and does not travel to the GPU box) on the host cores, bounded sample per step."""
     if rank != 0:
         return
+    if a.mode == "train":
+        return run_reference_train(a, w, out)
     from lsnf_b200 import synth
     gsd = synth.generator_state(w["dataset"], w["nz"], w["ngf"], 3, seed=1)
     fsd = synth.flow_state(w["nz"], w["f_width"], 5, 1, 2, seed=1)
@@ -240,6 +267,42 @@ def run_reference(a, w, rank, out):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a.workload, w),
             "details": {"noise": "none needed for timing (torch CPU oracle)", "cpu": cpu_model()},
+            "cpu_baseline": {"value": value, "unit": "latent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    out.emit(line)
+
+
+def run_reference_train(a, w, out):
+    """--impl reference --mode train: one whole training iteration of the reference (train.py:376-415: Langevin call,
+    generator step, flow step) on the host cores -- BASELINE.json's config 1 is exactly this on the SVHN shape.  Each
+    step times a bounded sample of the Langevin call (REF_SAMPLE_T iterations; the per-iteration cost does not depend
+    on T) plus the two parameter updates in full; the iteration time is sample * T / REF_SAMPLE_T + updates."""
+    from lsnf_b200 import synth
+    gsd = synth.generator_state(w["dataset"], w["nz"], w["ngf"], 3, seed=1)
+    fsd = synth.flow_state(w["nz"], w["f_width"], 5, 1, 2, seed=1)
+    sample_T, B, T = REF_SAMPLE_T[a.workload], w["B"], w["T"]
+    for _ in range(max(a.warmup, 1) - 1):
+        oracle_rate(w, gsd, fsd, 1, batch=B)
+    t0 = time.perf_counter()
+    t_langevin = t_update = 0.0
+    threads = os.cpu_count() or 1
+    for _ in range(a.steps):
+        _, dt, threads, _ = oracle_rate(w, gsd, fsd, sample_T, batch=B)
+        t_langevin += dt * T / sample_T
+        t_update += oracle_update_seconds(w, gsd, fsd, B, threads, repeats=1)
+    iter_s = (t_langevin + t_update) / a.steps
+    value = B * T / iter_s
+    sample = (f"each step times {sample_T} of the {T} Langevin iterations of a batch of {B} (scaled by {T}/{sample_T}: "
+              f"the per-iteration cost of the loop does not depend on T) and one full generator + flow update "
+              f"(autograd + torch Adam) on {cpu_model()}")
+    line = {"impl": "reference", "metric": "train_iteration_latent_steps_per_sec", "value": value,
+            "unit": "latent-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * iter_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "mode": "train",
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a.workload, w),
+            "details": {"what": "Langevin + generator update + flow update (train.py:376-415) on the torch CPU oracle",
+                        "ms_per_iteration": 1e3 * iter_s, "langevin_call_ms": 1e3 * t_langevin / a.steps,
+                        "updates_ms": 1e3 * t_update / a.steps, "cpu": cpu_model()},
             "cpu_baseline": {"value": value, "unit": "latent-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}

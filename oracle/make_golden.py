@@ -77,6 +77,85 @@ def reference_langevin(netG, netF, z, x, steps, step_size, sigma, eps):
     return z.detach(), gn, fn
 
 
+def reference_parameter_updates(netG, netF, optG, optF, z_k, x):
+    """train.py:390-415 around the reference modules and torch.optim.Adam."""
+    mse = torch.nn.MSELoss(reduction="sum")
+    optG.zero_grad()
+    x_hat = netG(z_k.detach())
+    loss_g = mse(x_hat, x) / x.shape[0]
+    loss_g.backward()
+    optG.step()
+    optF.zero_grad()
+    z1, logdet, _ = netF(torch.squeeze(z_k), objective=torch.zeros(int(z_k.shape[0])), init=False)
+    prior_ll = -0.5 * (z1 ** 2)
+    prior_ll = prior_ll.flatten(1).sum(-1) + np.log(2 * np.pi)
+    ll = prior_ll + logdet
+    loss_f = -ll.mean()
+    loss_f.backward()
+    optF.step()
+    return loss_g.detach(), loss_f.detach()
+
+
+TRAIN_CASE = dict(dataset="svhn", nz=100, ngf=32, f_width=64, B=6, T=4, sigma=0.3, coupling=1, lr=0.0004, iters=2)
+TRAIN_KEEP = ["gen.9.weight", "gen.9.bias", "gen.0.bias", "revnet2d_s.0.revnet2d_step_s.0.invertible_1x1_conv.w",
+              "revnet2d_s.0.revnet2d_step_s.0.actnorm.logs", "revnet2d_s.0.revnet2d_step_s.4.f.fc_zeros.b",
+              "revnet2d_s.0.revnet2d_step_s.2.f.fc_1.w"]
+
+
+def training_iteration_case(ref_model, out_dir):
+    """Two whole training iterations (train.py:384-415: Langevin, generator step, flow step; Adam as train.py:294-295)
+    on the reference modules against ``refpath.langevin`` + ``refpath.parameter_updates`` on plain leaf tensors."""
+    c = TRAIN_CASE
+    args = ref_args(c)
+    gsd = synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=1)
+    fsd = synth.flow_state(c["nz"], c["f_width"], 5, c["coupling"], 2, seed=1)
+    netG, netF = ref_model._netG(args), ref_model._netF(args, nz=c["nz"])
+    netG.load_state_dict(to_torch(gsd))
+    netF.load_state_dict(to_torch(fsd))
+    adam = lambda ps: torch.optim.Adam(ps, lr=c["lr"], weight_decay=0, betas=(0.5, 0.999))
+    optG, optF = adam(netG.parameters()), adam(netF.parameters())
+    gp = {k: v.clone().requires_grad_(True) for k, v in to_torch(gsd).items()}
+    fp = to_torch(fsd)
+    fkeys = refpath.trainable_flow_keys(fp)
+    for k in fkeys:
+        fp[k] = fp[k].clone().requires_grad_(True)
+    o_optG, o_optF = adam(list(gp.values())), adam([fp[k] for k in fkeys])
+    layers = refpath.generator_layers(c["dataset"], c["nz"], c["ngf"], 3)
+    losses = []
+    for it in range(c["iters"]):
+        x_np, z0_np, eps_np = synth.inputs(c["B"], c["nz"], 3, 32, c["T"], seed=100 + it)
+        x, z0, eps = torch.from_numpy(x_np), torch.from_numpy(z0_np), torch.from_numpy(eps_np)
+        z_k, _, _ = reference_langevin(netG, netF, z0, x, c["T"], 0.1, c["sigma"], eps)
+        lg, lf = reference_parameter_updates(netG, netF, optG, optF, z_k, x)
+        o_zk, _, _ = refpath.langevin(z0, x, {k: v.detach() for k, v in gp.items()}, {k: v.detach() for k, v in fp.items()},
+                                      layers, depth=5, steps=c["T"], step_size=0.1, sigma=c["sigma"], eps=eps)
+        o_lg, o_lf = refpath.parameter_updates(gp, fp, o_zk, x, layers, o_optG, o_optF, depth=5)
+        close(o_zk, z_k, 1e-6, "z_k")
+        close(o_lg, lg, 1e-6, "loss_g")
+        close(o_lf, lf, 1e-6, "loss_f")
+        losses.append([lg.item(), lf.item()])
+    rg, rf = netG.state_dict(), netF.state_dict()
+    worst = 0.0
+    for k in gp:
+        worst = max(worst, close(gp[k].detach(), rg[k], 1e-6, k))
+    for k in fp:
+        if fp[k].is_floating_point():
+            # ``actnorm.bias`` is the same Parameter as ``actnorm.b`` in the module (model.py:231): a plain dict holds
+            # two tensors, only ``b`` is read and updated
+            src = k[:-len("bias")] + "b" if k.endswith("actnorm.bias") else k
+            worst = max(worst, close(fp[src].detach(), rf[k], 1e-6, k))
+    moved = max(float((rg[k] - to_torch(gsd)[k]).abs().max()) for k in gp)
+    print("train_update", "losses", losses, "parameters after", c["iters"], "iterations: max rel err", worst,
+          "largest generator update", moved)
+    out = dict(config=np.array(repr(c)), losses=np.array(losses, np.float64),
+               g_checksum_after=np.array(synth.checksum({k: v.numpy() for k, v in rg.items()})),
+               f_checksum_after=np.array(synth.checksum({k: v.numpy() for k, v in rf.items() if v.is_floating_point()})))
+    for k in TRAIN_KEEP:
+        out["after:" + k] = (rg[k] if k in rg else rf[k]).numpy()
+    np.savez_compressed(os.path.join(out_dir, "train_update_svhn_small.npz"), **out)
+    print("wrote train_update_svhn_small")
+
+
 def close(a, b, tol, what):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
@@ -168,6 +247,7 @@ def main():
         keys["gen_" + ds] = [f"{k}:{tuple(v.shape)}" for k, v in m.state_dict().items()]
     np.savez_compressed(os.path.join(out_dir, "state_dict_keys.npz"), **{k: np.array(v) for k, v in keys.items()})
     print("wrote state_dict_keys")
+    training_iteration_case(ref_model, out_dir)
 
 
 if __name__ == "__main__":

@@ -202,6 +202,40 @@ def langevin(z0: torch.Tensor, x: torch.Tensor, gp: Params, fp: Params, layers, 
     return z.detach(), gn, fn
 
 
+def trainable_flow_keys(fp: Params) -> List[str]:
+    """Keys of the flow ``state_dict`` that ``optF`` owns and that receive a gradient: every float tensor except the
+    ``actnorm.bias`` aliases of ``actnorm.b`` (model.py:231 registers the same Parameter twice) and the ``fc.b`` the
+    forward pass never reads (model.py:329-330; its .grad stays None, Adam skips it)."""
+    return [k for k in fp if fp[k].is_floating_point() and not k.endswith("actnorm.bias")
+            and not (k.endswith(".b") and (".fc_1." in k or ".fc_2." in k) and "actnorm" not in k)]
+
+
+def parameter_updates(gp: Params, fp: Params, z_k: torch.Tensor, x: torch.Tensor, layers, optG, optF, *, depth: int,
+                      leak: float = 0.2, coupling: int = 1, permutation: int = 2,
+                      g_max_norm: Optional[float] = None, f_max_norm: Optional[float] = None):
+    """The two parameter updates that follow the Langevin call in one training iteration (train.py:390-415).
+
+    ``gp`` / ``fp`` map state_dict keys to LEAF tensors with ``requires_grad`` that ``optG`` / ``optF``
+    (``torch.optim.Adam``, train.py:294-295) were built on.  Returns (loss_g, loss_f) as 0-d tensors.
+    """
+    bsz = x.shape[0]
+    optG.zero_grad()                                                                     # train.py:390
+    x_hat = generator_forward(gp, z_k.detach(), layers, leak)                            # :392
+    loss_g = F.mse_loss(x_hat, x, reduction="sum") / bsz                                 # :393
+    loss_g.backward()                                                                    # :394
+    if g_max_norm is not None:                                                           # :396-397 (intended: args.g_max_norm)
+        torch.nn.utils.clip_grad_norm_([v for v in gp.values() if v.grad is not None], g_max_norm)
+    optG.step()                                                                          # :398
+    optF.zero_grad()                                                                     # :403
+    ll, _z1, _ld = log_prior(fp, torch.squeeze(z_k.detach()).reshape(bsz, -1), depth, coupling, permutation)  # :405-409
+    loss_f = -ll.mean()                                                                  # :410
+    loss_f.backward()                                                                    # :411
+    if f_max_norm is not None:                                                           # :412-413
+        torch.nn.utils.clip_grad_norm_([v for v in fp.values() if v.grad is not None], f_max_norm)
+    optF.step()                                                                          # :415
+    return loss_g.detach(), loss_f.detach()
+
+
 def recon_grad(z: torch.Tensor, x: torch.Tensor, gp: Params, layers, sigma: float, leak: float = 0.2):
     """One evaluation of train.py:312-314: (x_hat, d/dz [1/(2 sigma^2) * sum (G(z)-x)^2])."""
     z = z.clone().detach().requires_grad_(True)

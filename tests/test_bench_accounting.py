@@ -64,3 +64,27 @@ def test_library_stage_flops_are_nominal_and_never_below_the_algorithmic_ones(na
         assert fwd_nominal / 1e6 <= NOMINAL_MFLOP[name] * 1.35
     finally:
         lib.lsnf_plan_destroy(h)
+
+
+def test_reference_arm_times_one_whole_training_iteration_of_config_1():
+    """`bench.py --impl reference --mode train --workload svhn`: BASELINE.json's config 1 ("one training iteration on
+    CPU: flow prior + short-run Langevin + generator update") on the host cores, same JSON contract as the CUDA arm's
+    `--mode train` line."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--mode", "train",
+                        "--workload", "svhn", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_iteration_latent_steps_per_sec"
+    assert line["mode"] == "train" and line["gpu_launches"] == 0 and line["higher_is_better"] is True
+    assert line["config"] == bench.workload_config("svhn", bench.WORKLOADS["svhn"])
+    d = line["details"]
+    assert d["ms_per_iteration"] == pytest.approx(d["langevin_call_ms"] + d["updates_ms"], rel=1e-9)
+    assert line["value"] == pytest.approx(100 * 20 / (d["ms_per_iteration"] * 1e-3), rel=1e-9)
+    assert d["langevin_call_ms"] > d["updates_ms"] > 0           # SURVEY section 6: 1 467 ms against 110 ms on 8 vCPU
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

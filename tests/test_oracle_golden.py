@@ -54,6 +54,46 @@ def test_oracle_matches_reference_fixture(name):
     assert rel_err(g["z_T"], g["z_T_fp64"]) < 1e-5
 
 
+def test_parameter_updates_match_the_reference_training_iterations_fixture():
+    # two whole training iterations of train.py:384-415 run on the reference's own modules + torch Adam
+    # (oracle/make_golden.py: training_iteration_case): refpath.langevin + refpath.parameter_updates must land on the
+    # same losses and the same parameters
+    from oracle.make_golden import TRAIN_CASE as c, TRAIN_KEEP
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_update_svhn_small.npz"))
+    gsd = synth.generator_state(c["dataset"], c["nz"], c["ngf"], 3, seed=1)
+    fsd = synth.flow_state(c["nz"], c["f_width"], 5, c["coupling"], 2, seed=1)
+    gp = {k: v.clone().requires_grad_(True) for k, v in to_torch(gsd).items()}
+    fp = to_torch(fsd)
+    fkeys = refpath.trainable_flow_keys(fp)
+    assert len(fkeys) == 60                        # 12 trainable tensors per step that receive a gradient
+    for k in fkeys:
+        fp[k] = fp[k].clone().requires_grad_(True)
+    adam = lambda ps: torch.optim.Adam(ps, lr=c["lr"], weight_decay=0, betas=(0.5, 0.999))
+    optG, optF = adam(list(gp.values())), adam([fp[k] for k in fkeys])
+    layers = refpath.generator_layers(c["dataset"], c["nz"], c["ngf"], 3)
+    for it in range(c["iters"]):
+        x_np, z0_np, eps_np = synth.inputs(c["B"], c["nz"], 3, 32, c["T"], seed=100 + it)
+        x, z0, eps = torch.from_numpy(x_np), torch.from_numpy(z0_np), torch.from_numpy(eps_np)
+        zk, _, _ = refpath.langevin(z0, x, {k: v.detach() for k, v in gp.items()}, {k: v.detach() for k, v in fp.items()},
+                                    layers, depth=5, steps=c["T"], step_size=0.1, sigma=c["sigma"], eps=eps)
+        lg, lf = refpath.parameter_updates(gp, fp, zk, x, layers, optG, optF, depth=5)
+        assert abs(lg.item() - g["losses"][it][0]) < 1e-5 * abs(g["losses"][it][0])
+        assert abs(lf.item() - g["losses"][it][1]) < 1e-5 * abs(g["losses"][it][1])
+    # Adam moves every element by ~lr per step whatever the size of its gradient, so an element whose gradient is
+    # within rounding of zero may land one update away on another CPU: bound the outliers, compare the bulk tightly
+    lr, n_it = c["lr"], c["iters"]
+    for k in TRAIN_KEEP:
+        got = (gp[k] if k in gp else fp[k]).detach()
+        want = torch.from_numpy(g["after:" + k])
+        d = (got - want).abs()
+        assert float(d.max()) <= 2.5 * lr * n_it, k
+        assert float((d > 1e-6).float().mean()) < 2e-3, k
+    after_g = synth.checksum({k: v.detach().numpy() for k, v in gp.items()})
+    np.testing.assert_allclose(after_g, g["g_checksum_after"], rtol=1e-5)
+    start = to_torch(gsd)
+    assert max(float((gp[k].detach() - start[k]).abs().max()) for k in gp) > 0.5 * lr      # the parameters did move
+
+
 def test_analytic_prior_gradient_matches_autograd_fp64():
     fsd = synth.flow_state(100, 64, 5, 1, 2, seed=3)
     rng = np.random.default_rng(0)
