@@ -82,9 +82,9 @@ typedef struct lsnf_config {
   float leak;            /* --g_activation_leak of the LeakyReLU (0.2) */
   int32_t gemm_impl;     /* lsnf_gemm_impl */
   int32_t bwd_passes;    /* tensor-core passes of the data-gradient stages: 0 or 3 (default) = bf16 hi|lo split, 3 MMAs
-                            per K step: arithmetic not narrower than the reference's fp32.  1 = explicit opt-in to a
-                            single fp16 pass (11-bit significands, gradient good to ~2e-4): a reduced-precision mode,
-                            measured margins in DESIGN.md section 4.1 */
+                            per K step, 16 significant bits per operand: z_T at the reference's own fp32 noise floor.
+                            1 = explicit opt-in to a single fp16 pass (11-bit significands, gradient good to ~2e-4): a
+                            reduced-precision mode, measured margins in DESIGN.md section 4.1 */
   int32_t train;         /* != 0: the workspace also holds the buffers of lsnf_generator_param_grads (transposed
                             operands and split-K partials of the weight-gradient GEMMs); 0 for inference-only plans */
   int32_t reserved[3];

@@ -323,7 +323,7 @@ _PLANS: Dict[Tuple, Plan] = {}
 def default_bwd_passes(noisy_chain: bool = False) -> int:
     """Tensor-core passes of the data-gradient stages (include/lsnf.h).
 
-    Always 3 (bf16 hi|lo split, arithmetic not narrower than the reference's fp32 autograd) unless the caller opts
+    Always 3 (bf16 hi|lo split, 16 significant bits per operand: z_T at the reference's own fp32 noise floor) unless the caller opts
     in to the single fp16 pass with ``bwd_passes=1`` / ``LSNF_BWD_PASSES=1``: that mode is ~1.4x faster end to end
     but carries an 11-bit significand through the gradient (measured margins on z_T against the 1e-4 budget:
     profiles/r2_parity_cifar10_b100_t40.json).  ``noisy_chain`` is kept for call compatibility and ignored."""
