@@ -100,19 +100,24 @@ def synthetic_batch(args, batch, device, generator):
     return torch.rand(batch, args.nc, args.img_size, args.img_size, device=device, generator=generator) * 2.0 - 1.0
 
 
-def require_cuda():
+def cuda_device(local_rank: int) -> torch.device:
+    """This rank's GPU, made current.  No GPU -> error: the lsnf_b200 path has no CPU fallback."""
     if not torch.cuda.is_available():
         raise RuntimeError("run_synthetic.py needs a CUDA device: the lsnf_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    return torch.device("cuda", local_rank)
+
+
+def device_sync(device) -> None:
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 def train(args):
     import torch.distributed as dist
-    require_cuda()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
+    device = cuda_device(int(os.environ.get("LOCAL_RANK", "0")))
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     set_seed(args.seed)                      # every rank builds the same parameters
@@ -143,7 +148,7 @@ def train(args):
                           fn.item(), optG.param_groups[0]["lr"], optF.param_groups[0]["lr"]), flush=True)
         schedG.step()                                                              # train.py:484-485
         schedF.step()
-        torch.cuda.synchronize()
+        device_sync(device)
         if rank == 0:
             dt = time.perf_counter() - t0
             print(f"epoch {epoch}: {args.iters_per_epoch} iterations in {dt:.2f} s = "
@@ -160,9 +165,7 @@ def train(args):
 
 
 def test(args):
-    require_cuda()
-    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(device)
+    device = cuda_device(int(os.environ.get("LOCAL_RANK", "0")))
     set_seed(args.seed)
     netG, netF = build(args, device)
     if args.path_check_point:
@@ -172,13 +175,13 @@ def test(args):
     # train.py:565-586: n_fid_samples prior samples in batches of batch_size, already mapped to [0, 1]
     n_batches = max(1, args.n_fid_samples // args.batch_size)
     rng = torch.Generator(device).manual_seed(args.seed)
-    torch.cuda.synchronize()
+    device_sync(device)
     t0 = time.perf_counter()
     stats = torch.zeros(2, device=device)
     for _ in range(n_batches):
         xs = lsnf_b200.sample_x(netG, netF, args.batch_size, device, generator=rng)
         stats += torch.stack([xs.mean(), xs.var()])
-    torch.cuda.synchronize()
+    device_sync(device)
     dt = time.perf_counter() - t0
     m, v = (stats / n_batches).tolist()
     print(f"{n_batches * args.batch_size} prior samples in {dt:.3f} s = {n_batches * args.batch_size / dt:,.0f} samples/s; "

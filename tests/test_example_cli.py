@@ -76,3 +76,55 @@ def test_without_a_gpu_the_script_stops_instead_of_falling_back():
         ex.main("--dataset svhn --nz 100 --ngf 8 --n_epochs 1 --iters_per_epoch 1".split())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ex.main("--dataset svhn --nz 100 --ngf 8 --test_mode".split())
+
+
+def test_train_and_test_loops_run_end_to_end_with_the_device_calls_stubbed(tmp_path, monkeypatch, capsys):
+    """The script's own logic -- epochs, the reference's log line, ExponentialLR per epoch, checkpoint files, resume,
+    test mode -- with lsnf_b200's three device entry points replaced by CPU recorders (the entry points themselves are
+    covered by the GPU suite)."""
+    calls = {"train": [], "sample": 0, "recon": 0}
+
+    def fake_iteration(x, netG, netF, optG, optF, args, **kw):
+        calls["train"].append(dict(batch=x.shape[0], **{k: kw[k] for k in ("global_batch", "sample_offset", "seed")}))
+        for opt in (optG, optF):          # what fused_step does, as far as the schedulers and checkpoints can tell
+            for grp in opt.param_groups:
+                for p in grp["params"]:
+                    p.grad = torch.zeros_like(p)
+            opt.step()
+        return torch.tensor(10.0), torch.tensor(5.0), torch.tensor(1.0), torch.tensor(2.0), None
+
+    def fake_sample_x(netG, netF, n, device, generator=None, **kw):
+        calls["sample"] += 1
+        return torch.rand(n, 3, 32, 32, generator=generator)
+
+    def fake_recon(batches, netG, netF, args, generator=None):
+        calls["recon"] += sum(1 for _ in batches)
+        return 0.125
+
+    monkeypatch.setattr(ex, "cuda_device", lambda local: torch.device("cpu"))
+    monkeypatch.setattr(lsnf_b200, "training_iteration", fake_iteration)
+    monkeypatch.setattr(lsnf_b200, "sample_x", fake_sample_x)
+    monkeypatch.setattr(lsnf_b200, "reconstruction_error", fake_recon)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    ckpt = tmp_path / "ckpt"
+    base = f"--dataset svhn --nz 100 --ngf 8 --batch_size 12 --iters_per_epoch 3 --n_printout 2 --ckpt_dir {ckpt}"
+    ex.main((base + " --n_epochs 2 --g_gamma 0.5").split())
+    out = capsys.readouterr().out
+    assert len(calls["train"]) == 6 and calls["train"][0] == dict(batch=12, global_batch=12, sample_offset=0, seed=1 << 32)
+    assert len({c["seed"] for c in calls["train"]}) == 6                      # a fresh noise seed every iteration
+    assert "loss_g=  10.000, loss_f=   5.000, z_g_grad_norm=   1.000, z_f_grad_norm=   2.000" in out
+    assert "lr_g=0.000400" in out and "lr_g=0.000200" in out                   # ExponentialLR stepped once per epoch
+    assert sorted(os.listdir(ckpt)) == ["ckpt_000000.pth", "ckpt_000001.pth"]
+    ck = torch.load(ckpt / "ckpt_000001.pth")
+    assert ck["epoch"] == 1 and ck["optG"]["param_groups"][0]["lr"] == pytest.approx(0.0001)
+    # resume (train.py:342-349): continues at epoch 2 with the optimizer state of the checkpoint
+    calls["train"].clear()
+    ex.main((base + f" --n_epochs 3 --path_check_point {ckpt / 'ckpt_000001.pth'}").split())
+    assert len(calls["train"]) == 3 and "ckpt_000002.pth" in os.listdir(ckpt)
+    # test mode (train.py:520-662): n_fid_samples / batch_size sampling calls, then the reconstruction report
+    ex.main((base + f" --test_mode --testing_reconstruct --n_fid_samples 48 --n_test_batches 2 "
+                    f"--path_check_point {ckpt / 'ckpt_000002.pth'}").split())
+    out = capsys.readouterr().out
+    assert calls["sample"] == 4 and calls["recon"] == 2
+    assert "48 prior samples" in out and "reconstruction error=0.125" in out
