@@ -19,8 +19,8 @@ output directory).  What runs:
   ``g_l_steps * 20`` noise-free Langevin iterations per batch (train.py:606, :641-662).
 
 Status: written in the last session of round 2 after the GPU budget was spent -- the host side (flags, network
-construction, checkpoints, the no-GPU error) is covered by tests/test_example_cli.py on the CPU; the GPU legs have NOT
-been executed on a B200.  They only call entry points that the GPU suite exercises with the same arguments
+construction, checkpoints, resume, the epoch / test-mode loops with the device entry points stubbed, the no-GPU error)
+is covered by tests/test_example_cli.py on the CPU; the GPU legs have NOT been executed on a B200.  They only call entry points that the GPU suite exercises with the same arguments
 (``training_iteration``: tests/test_gpu_langevin.py, tools/train_ddp_check.py; ``sample_x`` / ``reconstruction_error``:
 tests/test_gpu_langevin.py, tests/test_gpu_sampling_and_long_chains.py).
 
